@@ -1,0 +1,178 @@
+/*
+ * lda_b200.h -- C ABI of liblda_b200.so: B200 (sm_100a) implementation of the LDA SCVB0
+ * path of james-bowman/nlp (lda.go).  This is the library a Go shim binds through cgo
+ * (INTEGRATION.md shows the binding); there are no C++/torch types in any signature.
+ *
+ * The reference has no FFI boundary of its own (it is pure Go).  Each entry point below
+ * therefore cites the Go method/field of `nlp.LatentDirichletAllocation` it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - every function returns 0 on success or an lda_b200_status code; text via
+ *    lda_b200_last_error().  Nothing aborts or exits the host process.
+ *  - all pointers are host pointers owned by the caller; inputs are read-only; nothing is
+ *    retained after the call returns (cgo pointer rules); outputs are caller-allocated.
+ *  - the term x document matrix is passed as CSC: indptr[D+1], ind[nnz] (row = word id),
+ *    data[nnz]; int64 = Go `int`, double = Go `float64` (what sparse.CSC / ToCSC() hold,
+ *    lda.go:464-466).  A dense mat.Matrix is passed as the CSC listing each column's
+ *    non-zero rows in ascending order (utils.go:51-57).  Token order inside a document is
+ *    preserved exactly (it matters: updates inside a document are sequential).
+ *  - doc-topic results are K x D row-major float64 (lda.go:452,541), components are
+ *    K x W row-major float64 (lda.go:415).
+ *  - one handle = one model on one GPU, used by one caller at a time.  With a
+ *    communicator of R ranks (lda_b200_comm_init) each rank owns the global minibatches
+ *    m with m % R == rank (lda.go:504-528 hands consecutive minibatches to workers);
+ *    every rank is given the same global indptr, and reads only the ranges of ind/data
+ *    (and writes only the columns of theta_out) that belong to its own minibatches.
+ */
+#ifndef LDA_B200_H
+#define LDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    LDA_B200_OK = 0,
+    LDA_B200_EINVAL = 1,      /* bad argument (NULL, negative size, word id out of range, ...) */
+    LDA_B200_ECUDA = 2,       /* CUDA runtime error (incl. no device) */
+    LDA_B200_ENCCL = 3,       /* NCCL error or libnccl.so.2 not loadable */
+    LDA_B200_EUNSUPPORTED = 4,/* e.g. K > 1024 */
+    LDA_B200_ESTATE = 5       /* call needs a fitted model (Transform before Fit) */
+} lda_b200_status;
+
+/* nlp.LearningSchedule, lda.go:16-32 */
+typedef struct {
+    double S, Tau, Kappa;
+} lda_b200_schedule;
+
+/* exported fields of nlp.LatentDirichletAllocation, lda.go:68-134; defaults lda.go:160-186 */
+typedef struct {
+    int32_t K;                              /* lda.go:85  */
+    int32_t iterations;                     /* lda.go:70  Iterations */
+    int32_t batch_size;                     /* lda.go:82  BatchSize */
+    int32_t burn_in_passes;                 /* lda.go:89  BurnInPasses */
+    int32_t transformation_passes;          /* lda.go:93  TransformationPasses */
+    int32_t perplexity_evaluation_frequency;/* lda.go:79  */
+    int32_t change_evaluation_frequency;    /* lda.go:103 */
+    int32_t processes;                      /* lda.go:134 Processes: informational; the degree of
+                                               parallelism is the communicator size */
+    double perplexity_tolerance;            /* lda.go:75  */
+    double mean_change_tolerance;           /* lda.go:98  */
+    double alpha, eta;                      /* lda.go:106,109 */
+    lda_b200_schedule rho_phi, rho_theta;   /* lda.go:112,115 */
+} lda_b200_config;
+
+/* private scalar state of the Go struct that survives between calls (lda.go:117-121).
+ * The Go shim keeps these in its struct and passes them in/out of each call. */
+typedef struct {
+    double rho_phi_t;       /* lda.go:117; reset to 1 by every fit (lda.go:497) */
+    double rho_theta_t;     /* lda.go:118; never reset, ++ per iteration (lda.go:502) */
+    double words_in_corpus; /* lda.go:120; accumulated with += and never reset (lda.go:481) */
+} lda_b200_counters;
+
+/* state of golang.org/x/exp/rand's PCGSource (128-bit; PCGSource.MarshalBinary order is
+ * high then low).  Used for `Rnd` (lda.go:126) when the caller lets the library draw the
+ * initial nPhi / nTheta on the device instead of passing them. */
+typedef struct {
+    uint64_t high, low;
+} lda_b200_pcg;
+
+typedef struct lda_b200_handle lda_b200_handle;
+
+/* fills the defaults of NewLatentDirichletAllocation(k), lda.go:145-189 */
+void lda_b200_default_config(int32_t k, lda_b200_config *out);
+
+/* NewLatentDirichletAllocation, lda.go:145: allocates the model on CUDA device `device`. */
+int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle **out);
+void lda_b200_destroy(lda_b200_handle *h);
+/* exported fields may be changed between calls in Go; K may not change after a fit. */
+int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg);
+/* error text of the last failed call on h (h == NULL: last failed create on this thread) */
+const char *lda_b200_last_error(const lda_b200_handle *h);
+
+/* Multi-GPU (replaces the goroutine pool, lda.go:487-528): one handle per GPU, one
+ * communicator over them.  id is a 128-byte ncclUniqueId produced by
+ * lda_b200_comm_unique_id on rank 0 and distributed by the host. */
+int lda_b200_comm_unique_id(void *id128);
+int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const void *id128);
+
+/* FitTransform, lda.go:463-542 (Fit, lda.go:211, is the same call with theta_out == NULL).
+ *  nphi0   W*K  values [w*K+k] replacing the draws of lda.go:199-205, or NULL
+ *  ntheta0 D*K  values [j*K+k] replacing the draws of lda.go:472-475, or NULL
+ *  rnd     if nphi0/ntheta0 is NULL the corresponding draws are taken from *rnd exactly as
+ *          Rnd.Int() % n would produce them, and *rnd is advanced by W*K (+ D*K) draws
+ *  ctr     in/out private counters (see lda_b200_counters)
+ *  theta_out   K*D doubles or NULL
+ *  perp_trace  receives every perplexity evaluated inside the fit (lda.go:530-539
+ *              computes them but does not expose them); perp_cap entries; may be NULL
+ *  n_evals, iters_run  optional outputs
+ */
+int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                 const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                 lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
+                 int32_t *iters_run);
+
+/* Transform, lda.go:446-453 (unNormalisedTransform lda.go:420-437 + normaliseTheta).
+ *  theta0  D*K values [j*K+k] replacing the draws of lda.go:422-426, or NULL (then *rnd)
+ *  rho_theta_t  the model's current rhoThetaT (burnInDoc uses it, lda.go:231)
+ *  passes_out   optional D entries: burn-in passes each document executed */
+int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                       const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *theta_out,
+                       int32_t *passes_out);
+
+/* Perplexity, lda.go:368-389 */
+int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                        const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out);
+
+/* Components, lda.go:414-416: out = K*W doubles */
+int lda_b200_components(lda_b200_handle *h, double *out);
+
+/* model persistence (absent in the reference: TODO at lda.go:158).  nphi = W*K [w*K+k],
+ * nz = K; raw un-normalised statistics (lda.go:137,140). */
+int lda_b200_get_dims(const lda_b200_handle *h, int64_t *W, int32_t *K);
+int lda_b200_get_state(lda_b200_handle *h, double *nphi, double *nz);
+int lda_b200_set_state(lda_b200_handle *h, int64_t W, const double *nphi, const double *nz);
+
+/* host-side restatement of Rnd.Int() % n draws (lda.go:201,425,474) for callers without
+ * golang.org/x/exp/rand: out[i] = float64(Int() % n) / float64(n); advances *rnd. */
+void lda_b200_pcg_seed(lda_b200_pcg *rnd, uint64_t seed);
+uint64_t lda_b200_pcg_uint64(lda_b200_pcg *rnd);
+void lda_b200_pcg_fill(lda_b200_pcg *rnd, int64_t count, int64_t n, double *out);
+void lda_b200_pcg_advance(lda_b200_pcg *rnd, uint64_t draws);
+
+/* Test/diagnostic hook for the "CSR/token handling is bit-exact" requirement: uploads the
+ * CSC exactly as lda_b200_fit does and reads the device representation back.
+ *  ind_out nnz int32, val_out nnz float, wc_out D doubles (lda.go:476-482), n_out = sum */
+int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                              const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
+                              double *wc_out, double *n_out);
+
+/* Resident-corpus API used by bench.py to time the fit loop with the inputs already in
+ * HBM (the `value` leg); lda_b200_fit is these three calls back to back. */
+int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                       const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                       lda_b200_counters *ctr);
+/* runs up to n_iterations more iterations of lda.go:501-540 on the resident corpus on the
+ * handle's stream; *stopped = 1 when the perplexity early stop fired.  elapsed_ms (optional)
+ * receives the CUDA-event time of the iterations on the launching stream. */
+int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_counters *ctr, double *perp_trace,
+                         int32_t perp_cap, int32_t *n_evals, int32_t *iters_run, int32_t *stopped,
+                         float *elapsed_ms);
+int lda_b200_fit_end(lda_b200_handle *h, double *theta_out);
+
+/* per-launch CUDA-event timing of the minibatch / blend kernels on the handle's stream (off by default) */
+int lda_b200_set_profiling(lda_b200_handle *h, int32_t on);
+/* number of kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t lda_b200_launch_count(const lda_b200_handle *h);
+/* CUDA-event time (ms) spent in the fused SCVB0 minibatch kernel during the last
+ * lda_b200_fit_iterate call, and the number of its launches (roofline leg of bench.py) */
+int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
+                              float *blend_ms, int32_t *blend_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDA_B200_H */

@@ -1,0 +1,569 @@
+// kernels.cuh -- hand-written sm_100a kernels of the LDA SCVB0 path (reference: lda.go).
+//
+// Layout in HBM (all fp32 unless stated):
+//   nPhi, nPhiHat  [W][Kp]   word-major, topic fastest (same as lda.go's [w*K+k]); Kp = K rounded up to 4
+//   nTheta         [Dl][Kp]  document-major, topic fastest (lda.go's [j*K+k]); Dl = documents owned by this GPU
+//   invZ           [Kp]      1/(nZ[k] + eta*W), 0 for the pad topics k >= K (this is what masks the pad)
+//   CSC            doc_ptr int64[Dl+1], ind int32[nnz], val fp32[nnz]   (token order preserved)
+//
+// Mapping: one document per "group" of LANES lanes (LANES = 32 for K > 64), each lane owning NV
+// float4 slices of the topic axis: slice v of lane g covers topics 4*(v*LANES+g) .. +3, so every
+// row access is a fully coalesced 128-bit load/reduction.  Tokens inside a document are a
+// sequential chain through nTheta[j,:] (lda.go:236 -> 247), so parallelism is documents x topics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ldab {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+
+// vector reduction into global memory: one 16-byte RED per lane instead of four scalar atomics
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <int LANES>
+__device__ __forceinline__ float group_sum(float x) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;  // xor butterfly: bitwise identical on every lane of the group
+}
+template <int LANES>
+__device__ __forceinline__ double group_sum_d(double x) {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+    return x;
+}
+
+struct DocsArgs {
+    const int64_t *doc_ptr;  // [Dl+1]
+    const int32_t *ind;
+    const float *val;
+    const float *wc;         // [Dl]  lda.go:476-480
+    float *theta;            // [Dl][Kp]
+    const float *nphi;       // [W][Kp]
+    float *nphi_hat;         // [W][Kp]   (main pass only)
+    const float *inv_z;      // [Kp]
+    const float *log1m_rho;  // [passes+1]: ln(1 - RhoTheta.Calc(rhoThetaT + c)), c = 0..passes
+    int32_t *passes_out;     // optional [Dl]
+    int *doc_counter;        // dynamic document scheduler (reset by the blend kernel / host)
+    int doc_begin, doc_end;  // local document range of this launch
+    int K, Kp;
+    int passes;              // burn-in passes (fit: BurnInPasses, transform: TransformationPasses)
+    int change_freq;         // ChangeEvaluationFrequency
+    float change_tol;        // MeanChangeTolerance
+    float alpha, eta;
+    float hat_scale;         // wordsInCorpus / batchSize (x allreduce coefficient), lda.go:293
+};
+
+// One pass over the tokens of the documents currently held by this warp's groups.
+//   Eqn 5 (lda.go:234-242 / 277-284): gamma_k ∝ (nPhi[i,k]+eta)(nTheta[j,k]+alpha)/(nZ[k]+eta*W), normalised
+//   Eqn 9 (lda.go:244-249 / 286-290): nTheta[j,k] = (1-rho)^v nTheta[j,k] + (1-(1-rho)^v) wc_j gamma_k
+//   MAIN  (lda.go:292-295):           nPhiHat[i,k] += N gamma_k / batchSize   (no factor v)
+// (1-rho)^v is evaluated once per token by the lane that loads it: q = 1-(1-rho)^v = -expm1(v ln(1-rho)),
+// which keeps full relative accuracy when rho is small (the reference calls math.Pow 2K times per token).
+template <int LANES, int NV, int P, bool MAIN>
+__device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int len, int maxlen, float l1m, float wcj,
+                                           int g, float4 (&th)[NV], const float4 (&iz)[NV], const bool (&ok)[NV]) {
+    for (int tile = 0; tile < maxlen; tile += LANES) {
+        const int my = tile + g;
+        const bool has = my < len;
+        const int wi = has ? a.ind[base + my] : -1;
+        const float q = has ? -expm1f(a.val[base + my] * l1m) : 0.f;
+        const int ntile = min(LANES, maxlen - tile);
+
+        float4 buf[P][NV];
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const int w = __shfl_sync(FULL, wi, s, LANES);
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (s < ntile && w >= 0 && ok[v]) buf[s][v] = ldg4(a.nphi + (int64_t)w * a.Kp + 4 * (v * LANES + g));
+        }
+        for (int t0 = 0; t0 < ntile; t0 += P) {
+#pragma unroll
+            for (int s = 0; s < P; ++s) {
+                const int t = t0 + s;
+                if (t < ntile) {  // warp-uniform
+                    const int w = __shfl_sync(FULL, wi, t, LANES);
+                    const float qt = __shfl_sync(FULL, q, t, LANES);
+                    float4 row[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) row[v] = buf[s][v];
+                    // refill this pipeline slot with the row of token t+P
+                    const int tn = t + P;
+                    const int wn = __shfl_sync(FULL, wi, tn & (LANES - 1), LANES);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (tn < ntile && wn >= 0 && ok[v])
+                            buf[s][v] = ldg4(a.nphi + (int64_t)wn * a.Kp + 4 * (v * LANES + g));
+
+                    float4 gm[NV];
+                    float part = 0.f;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        if (w >= 0 && ok[v]) {
+                            gm[v].x = (row[v].x + a.eta) * iz[v].x * (th[v].x + a.alpha);
+                            gm[v].y = (row[v].y + a.eta) * iz[v].y * (th[v].y + a.alpha);
+                            gm[v].z = (row[v].z + a.eta) * iz[v].z * (th[v].z + a.alpha);
+                            gm[v].w = (row[v].w + a.eta) * iz[v].w * (th[v].w + a.alpha);
+                        } else {
+                            gm[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        part += (gm[v].x + gm[v].y) + (gm[v].z + gm[v].w);
+                    }
+                    const float gsum = group_sum<LANES>(part);
+                    if (w >= 0) {
+                        const float r = 1.0f / gsum;
+                        const float keep = 1.0f - qt;
+                        const float mix = qt * wcj * r;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            th[v].x = fmaf(keep, th[v].x, mix * gm[v].x);
+                            th[v].y = fmaf(keep, th[v].y, mix * gm[v].y);
+                            th[v].z = fmaf(keep, th[v].z, mix * gm[v].z);
+                            th[v].w = fmaf(keep, th[v].w, mix * gm[v].w);
+                        }
+                        if (MAIN) {
+                            const float sc = a.hat_scale * r;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v)
+                                if (ok[v])
+                                    red_add_v4(a.nphi_hat + (int64_t)w * a.Kp + 4 * (v * LANES + g),
+                                               make_float4(sc * gm[v].x, sc * gm[v].y, sc * gm[v].z, sc * gm[v].w));
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// Fused SCVB0 kernel: burnInDoc (lda.go:218-261) for `passes` passes with its early exit, then (FIT) the
+// sufficient-statistics pass of fitMiniBatch (lda.go:274-297).  FIT = false is unNormalisedTransform's
+// per-document loop (lda.go:429-435).
+template <int LANES, int NV, int P, bool FIT>
+__global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
+    constexpr int GPW = 32 / LANES;  // documents per warp
+    const int lane = threadIdx.x & 31;
+    const int g = lane % LANES;
+    const int grp = lane / LANES;
+
+    bool ok[NV];
+    float4 iz[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ok[v] = 4 * (v * LANES + g) < a.Kp;
+        iz[v] = ok[v] ? ldg4(a.inv_z + 4 * (v * LANES + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+
+    for (;;) {
+        int d0 = 0;
+        if (lane == 0) d0 = atomicAdd(a.doc_counter, GPW);
+        d0 = __shfl_sync(FULL, d0, 0);
+        if (a.doc_begin + d0 >= a.doc_end) break;
+        const int doc = a.doc_begin + d0 + grp;
+        const bool valid = doc < a.doc_end;
+
+        int64_t base = 0;
+        int len = 0;
+        float wcj = 0.f;
+        if (valid) {
+            base = a.doc_ptr[doc];
+            len = (int)(a.doc_ptr[doc + 1] - base);
+            wcj = a.wc[doc];
+        }
+        float4 th[NV];
+        float *trow = a.theta + (int64_t)doc * a.Kp;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            th[v] = (valid && ok[v]) ? *reinterpret_cast<const float4 *>(trow + 4 * (v * LANES + g))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+
+        int maxlen = len;
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+
+        bool done = !valid;
+        int executed = 0;
+        double prev = 0.0;
+        for (int counter = 1; counter <= a.passes; ++counter) {
+            if (__all_sync(FULL, done)) break;
+            const bool chk = a.change_freq > 0 && counter % a.change_freq == 0;
+            if (chk && 1 < a.passes) {  // lda.go:224-230
+                double s = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s += ((double)th[v].x + th[v].y) + ((double)th[v].z + th[v].w);
+                prev = group_sum_d<LANES>(s);
+            }
+            const float l1m = a.log1m_rho[counter];  // lda.go:231
+            token_pass<LANES, NV, P, false>(a, base, done ? 0 : len, maxlen, l1m, wcj, g, th, iz, ok);
+            if (!done) executed = counter;
+            if (chk && counter < a.passes) {  // lda.go:251-259
+                double s = 0.0;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) s += ((double)th[v].x + th[v].y) + ((double)th[v].z + th[v].w);
+                s = group_sum_d<LANES>(s);
+                if (fabs(s - prev) / (double)a.K < (double)a.change_tol) done = true;
+            }
+        }
+        if (FIT) {
+            const float l1m = a.log1m_rho[a.passes];  // lda.go:274
+            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, g, th, iz, ok);
+        }
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v]) *reinterpret_cast<float4 *>(trow + 4 * (v * LANES + g)) = th[v];
+            if (a.passes_out && g == 0) a.passes_out[doc] = len > 0 ? executed : -1;
+        }
+    }
+}
+
+// ln(1 - S/(Tau + t0 + c)^Kappa), c = 0..n-1  (LearningSchedule.Calc, lda.go:30-32), evaluated in float64
+__global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, int n, float *out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) out[c] = (float)log1p(-S / pow(Tau + t0 + (double)c, Kappa));
+}
+
+// M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58):
+//   nPhi = A*nPhi + C*nPhiHat ; nPhiHat = 0 ; nZHat = colsum(nPhiHat) (== the reference's running sum, lda.go:295)
+// and, in the last block to finish: nZ = A*nZ + C*nZHat ; invZ = 1/(nZ + eta*W) ; scheduler reset.
+// blockDim.x = VPR*RPB with VPR = Kp/4 float4 per row, so a thread always owns the same 4 topics.
+struct BlendArgs {
+    float *nphi;
+    float *nphi_hat;
+    double *nz;      // [Kp]
+    double *nzhat;   // [Kp] scratch, zero on entry, zero on exit
+    float *inv_z;    // [Kp]
+    unsigned *ticket;
+    int *doc_counter;
+    int64_t W;
+    int K, Kp;
+    float A, C;
+    double Ad, Cd;
+    double etaW;
+};
+
+__global__ void __launch_bounds__(256) phi_blend_kernel(const BlendArgs a) {
+    extern __shared__ float4 sm4[];
+    const int VPR = a.Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < a.W; r += (int64_t)gridDim.x * RPB) {
+        float4 *pp = reinterpret_cast<float4 *>(a.nphi + r * a.Kp) + col;
+        float4 *hp = reinterpret_cast<float4 *>(a.nphi_hat + r * a.Kp) + col;
+        float4 p = *pp;
+        const float4 h = *hp;
+        p.x = fmaf(a.A, p.x, a.C * h.x);
+        p.y = fmaf(a.A, p.y, a.C * h.y);
+        p.z = fmaf(a.A, p.z, a.C * h.z);
+        p.w = fmaf(a.A, p.w, a.C * h.w);
+        *pp = p;
+        *hp = make_float4(0.f, 0.f, 0.f, 0.f);
+        acc.x += h.x;
+        acc.y += h.y;
+        acc.z += h.z;
+        acc.w += h.w;
+    }
+    sm4[threadIdx.x] = acc;
+    __syncthreads();
+    if (rslot == 0) {
+        double sx = 0, sy = 0, sz = 0, sw = 0;
+        for (int s = 0; s < RPB; ++s) {
+            const float4 t = sm4[s * VPR + col];
+            sx += t.x;
+            sy += t.y;
+            sz += t.z;
+            sw += t.w;
+        }
+        atomicAdd(a.nzhat + 4 * col + 0, sx);
+        atomicAdd(a.nzhat + 4 * col + 1, sy);
+        atomicAdd(a.nzhat + 4 * col + 2, sz);
+        atomicAdd(a.nzhat + 4 * col + 3, sw);
+    }
+    __shared__ bool last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        for (int k = threadIdx.x; k < a.Kp; k += blockDim.x) {
+            if (k < a.K) {
+                const double z = a.Ad * a.nz[k] + a.Cd * __ldcg(a.nzhat + k);
+                a.nz[k] = z;
+                a.inv_z[k] = (float)(1.0 / (z + a.etaW));
+            } else {
+                a.inv_z[k] = 0.f;
+            }
+            a.nzhat[k] = 0.0;
+        }
+        if (threadIdx.x == 0) {
+            *a.ticket = 0u;
+            *a.doc_counter = 0;
+        }
+    }
+}
+
+// invZ from nZ (after init / set_state)
+__global__ void inv_z_kernel(const double *nz, float *inv_z, int K, int Kp, double etaW) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < Kp) inv_z[k] = k < K ? (float)(1.0 / (nz[k] + etaW)) : 0.f;
+}
+
+// column sums over rows of a [R][Kp] fp32 matrix into double[Kp] (normalisePhi's sum, lda.go:351-356; init's
+// nZ, lda.go:203).  out must be zero on entry.  Same thread->column mapping as phi_blend_kernel.
+__global__ void __launch_bounds__(256) colsum_kernel(const float *src, int64_t R, int Kp, double *out) {
+    extern __shared__ float4 sm4[];
+    const int VPR = Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    double sx = 0, sy = 0, sz = 0, sw = 0;
+    for (int64_t r0 = (int64_t)blockIdx.x * RPB + rslot; r0 < R; r0 += (int64_t)gridDim.x * RPB * 64) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // short fp32 runs, flushed into float64
+        int64_t r = r0;
+        for (int i = 0; i < 64 && r < R; ++i, r += (int64_t)gridDim.x * RPB) {
+            const float4 t = ldg4(src + r * Kp + 4 * col);
+            acc.x += t.x;
+            acc.y += t.y;
+            acc.z += t.z;
+            acc.w += t.w;
+        }
+        sx += acc.x;
+        sy += acc.y;
+        sz += acc.z;
+        sw += acc.w;
+    }
+    double *smd = reinterpret_cast<double *>(sm4);
+    smd[4 * threadIdx.x + 0] = sx;
+    smd[4 * threadIdx.x + 1] = sy;
+    smd[4 * threadIdx.x + 2] = sz;
+    smd[4 * threadIdx.x + 3] = sw;
+    __syncthreads();
+    if (rslot == 0) {
+        for (int c = 0; c < 4; ++c) {
+            double s = 0;
+            for (int q = 0; q < RPB; ++q) s += smd[4 * (q * VPR + col) + c];
+            atomicAdd(out + 4 * col + c, s);
+        }
+    }
+}
+
+__global__ void reciprocal_kernel(const double *in, float *out, int K, int Kp) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < Kp) out[k] = k < K ? (float)(1.0 / in[k]) : 0.f;
+}
+
+// perplexity (lda.go:392-408) with normaliseTheta/normalisePhi (lda.go:323-363) folded in:
+//   dot = sum_k (nPhi[i,k]/colsum_k)(nTheta[j,k]/rowsum_j);  acc += log2(dot) * v     (float64 accumulation)
+struct PerpArgs {
+    const int64_t *doc_ptr;
+    const int32_t *ind;
+    const float *val;
+    const float *theta;
+    const float *nphi;
+    const float *inv_colsum;  // [Kp], 0 on the pad
+    double *acc;              // scalar
+    int n_docs;
+    int Kp;
+};
+
+template <int LANES, int NV, int P>
+__global__ void __launch_bounds__(256) perplexity_kernel(const PerpArgs a) {
+    constexpr int GPW = 32 / LANES;
+    const int lane = threadIdx.x & 31;
+    const int g = lane % LANES;
+    const int grp = lane / LANES;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    bool ok[NV];
+    float4 ic[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ok[v] = 4 * (v * LANES + g) < a.Kp;
+        ic[v] = ok[v] ? ldg4(a.inv_colsum + 4 * (v * LANES + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    double local = 0.0;
+    for (int d0 = warp * GPW; d0 < a.n_docs; d0 += nwarps * GPW) {
+        const int doc = d0 + grp;
+        const bool valid = doc < a.n_docs;
+        int64_t base = 0;
+        int len = 0;
+        if (valid) {
+            base = a.doc_ptr[doc];
+            len = (int)(a.doc_ptr[doc + 1] - base);
+        }
+        float4 tk[NV];
+        float part = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            tk[v] = (valid && ok[v]) ? ldg4(a.theta + (int64_t)doc * a.Kp + 4 * (v * LANES + g))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+            part += (tk[v].x + tk[v].y) + (tk[v].z + tk[v].w);
+        }
+        const float inv_rowsum = 1.0f / group_sum<LANES>(part);
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            tk[v].x *= ic[v].x * inv_rowsum;
+            tk[v].y *= ic[v].y * inv_rowsum;
+            tk[v].z *= ic[v].z * inv_rowsum;
+            tk[v].w *= ic[v].w * inv_rowsum;
+        }
+        int maxlen = len;
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+        for (int tile = 0; tile < maxlen; tile += LANES) {
+            const int my = tile + g;
+            const bool has = my < len;
+            const int wi = has ? a.ind[base + my] : -1;
+            const float vv = has ? a.val[base + my] : 0.f;
+            const int ntile = min(LANES, maxlen - tile);
+            float mine = 1.0f;  // dot of the token this lane loaded
+            for (int t0 = 0; t0 < ntile; t0 += P) {
+                float4 row[P][NV];
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                    const int w = __shfl_sync(FULL, wi, (t0 + s) & (LANES - 1), LANES);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        row[s][v] = (t0 + s < ntile && w >= 0 && ok[v]) ? ldg4(a.nphi + (int64_t)w * a.Kp + 4 * (v * LANES + g))
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                    float d = 0.f;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        d += (row[s][v].x * tk[v].x + row[s][v].y * tk[v].y) + (row[s][v].z * tk[v].z + row[s][v].w * tk[v].w);
+                    d = group_sum<LANES>(d);
+                    if (t0 + s == g) mine = d;
+                }
+            }
+            if (has) local += (double)log2f(mine) * (double)vv;
+        }
+    }
+    // block reduction of float64 partials
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(FULL, local, o);
+    if (lane == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        atomicAdd(a.acc, s);
+    }
+}
+
+// out[k*ld + col0 + r] = scale * src[r][k] as float64, for the K x D (lda.go:452,541) and K x W (lda.go:415)
+// outputs.  ROWNORM: divide by rowsum_r (normaliseTheta); else by col_sum[k] (normalisePhi); both in float64.
+// Block = 32 source rows; reads coalesced along k, writes coalesced along r.
+template <bool ROWNORM>
+__global__ void __launch_bounds__(256) transpose_out_kernel(const float *src, int64_t R, int K, int Kp, const double *col_sum,
+                                                            double *out, int64_t ld) {
+    __shared__ float tile[32][33];
+    __shared__ double rsum[32];
+    const int64_t r0 = (int64_t)blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (ROWNORM) {
+        for (int i = warp; i < 32; i += 8) {
+            const int64_t r = r0 + i;
+            double s = 0;
+            if (r < R)
+                for (int k = lane; k < K; k += 32) s += (double)src[r * Kp + k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+            if (lane == 0) rsum[i] = s;
+        }
+        __syncthreads();
+    }
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        for (int i = warp; i < 32; i += 8) {
+            const int64_t r = r0 + i;
+            tile[i][lane] = (r < R && k0 + lane < K) ? src[r * Kp + k0 + lane] : 0.f;
+        }
+        __syncthreads();
+        for (int kk = warp; kk < 32; kk += 8) {
+            const int k = k0 + kk;
+            const int64_t r = r0 + lane;
+            if (k < K && r < R) {
+                const double v = (double)tile[lane][kk];
+                out[(int64_t)k * ld + r] = ROWNORM ? v / rsum[lane] : v / col_sum[k];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- ingestion -------------------------------------------------------------------------------------
+// int64 word ids -> int32 (exact; ids outside [0,W) raise *err), float64 values -> fp32
+__global__ void narrow_ind_kernel(const int64_t *src, int32_t *dst, int64_t n, int64_t W, int *err) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = src[i];
+        if (w < 0 || w >= W) *err = 1;
+        dst[i] = (int32_t)w;
+    }
+}
+__global__ void narrow_val_kernel(const double *src, float *dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = (float)src[i];
+}
+__global__ void widen_f32_kernel(const float *src, double *dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = (double)src[i];
+}
+// [R][K] float64 (host layout, lda.go's [r*K+k]) <-> [R][Kp] fp32 with zero pad
+__global__ void pad_rows_kernel(const double *src, float *dst, int64_t R, int K, int Kp) {
+    const int64_t n = R * Kp;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / Kp;
+        const int k = (int)(i - r * Kp);
+        dst[i] = k < K ? (float)src[r * K + k] : 0.f;
+    }
+}
+__global__ void unpad_rows_kernel(const float *src, double *dst, int64_t R, int K, int Kp) {
+    const int64_t n = R * K;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / K;
+        const int k = (int)(i - r * K);
+        dst[i] = (double)src[r * Kp + k];
+    }
+}
+
+// wc[j] = sum of the document's values (lda.go:476-480), float64 accumulation; *n_total += sum_j wc[j] (lda.go:481)
+__global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, const float *val, int n_docs, float *wc,
+                                                     double *wc64, double *n_total) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    double tot = 0;
+    for (int d = warp; d < n_docs; d += nwarps) {
+        const int64_t b = doc_ptr[d], e = doc_ptr[d + 1];
+        double s = 0;
+        for (int64_t p = b + lane; p < e; p += 32) s += (double)val[p];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+        if (lane == 0) {
+            wc[d] = (float)s;
+            if (wc64) wc64[d] = s;
+            tot += s;
+        }
+    }
+    __shared__ double red[8];
+    if (lane == 0) red[threadIdx.x >> 5] = tot;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+        if (s != 0) atomicAdd(n_total, s);
+    }
+}
+
+}  // namespace ldab

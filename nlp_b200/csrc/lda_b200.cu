@@ -1,0 +1,1021 @@
+// lda_b200.cu -- engine + C ABI (include/lda_b200.h) of the B200 LDA SCVB0 path.
+// Reference behaviour: james-bowman/nlp lda.go (cited per function).  No CPU fallback: every
+// compute step is a kernel from kernels.cuh / pcg.cuh launched on the handle's stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/lda_b200.h"
+#include "kernels.cuh"
+#include "nccl_dl.h"
+#include "pcg.cuh"
+
+using namespace ldab;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Segment {
+    int64_t g0, g1;  // global document range
+    int64_t l0;      // first local row
+};
+
+// resident corpus shard + per-document statistics
+struct Corpus {
+    int64_t D = 0;       // global documents
+    int64_t Dl = 0;      // local documents
+    int64_t nnz = 0;     // local non-zeros
+    int64_t b = 0;       // block (minibatch) size used for sharding
+    std::vector<Segment> segs;
+    int64_t *doc_ptr = nullptr;
+    int32_t *ind = nullptr;
+    float *val = nullptr;
+    float *wc = nullptr;
+    float *theta = nullptr;
+    double n_local = 0;  // sum of values of the local shard
+    double n_global = 0;
+};
+
+struct EventPair {
+    cudaEvent_t a, b;
+    int kind;  // 0 = minibatch kernel, 1 = blend kernel
+};
+
+}  // namespace
+
+struct lda_b200_handle {
+    lda_b200_config cfg;
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+
+    // model (lda.go:137-140)
+    int64_t W = 0;
+    int K = 0, Kp = 0;
+    bool fitted = false;
+    float *nphi = nullptr;
+    double *nz = nullptr;
+    float *inv_z = nullptr;
+
+    // scratch
+    float *nphi_hat = nullptr;
+    double *nzhat = nullptr;
+    double *colsum = nullptr;
+    float *inv_colsum = nullptr;
+    unsigned *ticket = nullptr;
+    int *doc_counter = nullptr;
+    int *err_flag = nullptr;
+    double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
+    float *rho_tab = nullptr;
+    int rho_cap = 0;
+    void *stage = nullptr;
+    size_t stage_bytes = 0;
+    double *h_pinned = nullptr;  // small pinned read-back area
+
+    // fit run
+    Corpus fitc;
+    bool fit_open = false;
+    int32_t it_done = 0;
+    double prev_perplexity = 0;
+    bool stopped = false;
+
+    // comm
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+
+    // stats
+    int64_t launches = 0;
+    bool profiling = false;
+    std::vector<EventPair> ev_pool;
+    size_t ev_used = 0;
+    float mb_ms = 0, blend_ms = 0;
+    int mb_n = 0, blend_n = 0;
+};
+
+namespace {
+
+int fail(lda_b200_handle *h, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h)
+        h->err = buf;
+    else
+        g_create_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(h, LDA_B200_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (call);                                                                        \
+        if (r_ != ncclSuccess)                                                                           \
+            return fail(h, LDA_B200_ENCCL, "%s failed: %s", #call, nccl().GetErrorString(r_));            \
+    } while (0)
+#define TRY(call)            \
+    do {                     \
+        int rc_ = (call);    \
+        if (rc_) return rc_; \
+    } while (0)
+#define KCHECK()                      \
+    do {                              \
+        h->launches++;                \
+        CU(cudaPeekAtLastError());    \
+    } while (0)
+
+template <typename T>
+int dalloc(lda_b200_handle *h, T **p, size_t n) {
+    if (*p) {
+        cudaFree(*p);
+        *p = nullptr;
+    }
+    if (n == 0) n = 1;
+    CU(cudaMalloc((void **)p, n * sizeof(T)));
+    return 0;
+}
+template <typename T>
+void dfree(T **p) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+}
+
+void free_corpus(Corpus &c) {
+    dfree(&c.doc_ptr);
+    dfree(&c.ind);
+    dfree(&c.val);
+    dfree(&c.wc);
+    dfree(&c.theta);
+    c = Corpus();
+}
+
+inline int grid_for(int64_t n, int threads, int cap) {
+    int64_t g = (n + threads - 1) / threads;
+    if (g < 1) g = 1;
+    return (int)std::min<int64_t>(g, cap);
+}
+
+int validate_config(lda_b200_handle *h, const lda_b200_config *c) {
+    if (!c) return fail(h, LDA_B200_EINVAL, "config is NULL");
+    if (c->K < 1) return fail(h, LDA_B200_EINVAL, "K must be >= 1 (got %d)", c->K);
+    if (c->K > 1024) return fail(h, LDA_B200_EUNSUPPORTED, "K = %d > 1024 is not supported by this build", c->K);
+    if (c->batch_size < 1) return fail(h, LDA_B200_EINVAL, "BatchSize must be >= 1 (got %d)", c->batch_size);
+    if (c->burn_in_passes < 0 || c->transformation_passes < 0 || c->iterations < 0)
+        return fail(h, LDA_B200_EINVAL, "negative pass/iteration count");
+    return 0;
+}
+
+// ---- kernel dispatch on the topic width ------------------------------------------------------------
+template <bool FIT>
+int launch_docs(lda_b200_handle *h, const DocsArgs &a) {
+    const int vecs = a.Kp / 4;
+    const int n_docs = a.doc_end - a.doc_begin;
+    if (n_docs <= 0) return 0;
+    auto go = [&](auto kern, int lanes) -> int {
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
+        if (occ < 1) occ = 1;
+        const int gpw = 32 / lanes;
+        const int64_t warps = ((int64_t)n_docs + gpw - 1) / gpw;
+        const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * occ);
+        kern<<<grid, 256, 0, h->stream>>>(a);
+        KCHECK();
+        return 0;
+    };
+    if (vecs <= 4) return go(scvb0_docs_kernel<4, 1, 4, FIT>, 4);
+    if (vecs <= 8) return go(scvb0_docs_kernel<8, 1, 4, FIT>, 8);
+    if (vecs <= 16) return go(scvb0_docs_kernel<16, 1, 4, FIT>, 16);
+    if (vecs <= 32) return go(scvb0_docs_kernel<32, 1, 4, FIT>, 32);
+    if (vecs <= 64) return go(scvb0_docs_kernel<32, 2, 4, FIT>, 32);
+    if (vecs <= 128) return go(scvb0_docs_kernel<32, 4, 2, FIT>, 32);
+    return go(scvb0_docs_kernel<32, 8, 2, FIT>, 32);
+}
+
+int launch_perplexity(lda_b200_handle *h, const PerpArgs &a) {
+    const int vecs = a.Kp / 4;
+    if (a.n_docs <= 0) return 0;
+    auto go = [&](auto kern, int lanes) -> int {
+        const int gpw = 32 / lanes;
+        const int64_t warps = ((int64_t)a.n_docs + gpw - 1) / gpw;
+        const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * 8);
+        kern<<<grid, 256, 0, h->stream>>>(a);
+        KCHECK();
+        return 0;
+    };
+    if (vecs <= 4) return go(perplexity_kernel<4, 1, 4>, 4);
+    if (vecs <= 8) return go(perplexity_kernel<8, 1, 4>, 8);
+    if (vecs <= 16) return go(perplexity_kernel<16, 1, 4>, 16);
+    if (vecs <= 32) return go(perplexity_kernel<32, 1, 4>, 32);
+    if (vecs <= 64) return go(perplexity_kernel<32, 2, 4>, 32);
+    if (vecs <= 128) return go(perplexity_kernel<32, 4, 2>, 32);
+    return go(perplexity_kernel<32, 8, 2>, 32);
+}
+
+inline int blend_block(int Kp) {
+    const int vpr = Kp / 4;
+    return vpr * std::max(1, 256 / vpr);
+}
+
+// ---- profiling events ---------------------------------------------------------------------------------
+int ev_begin(lda_b200_handle *h, int kind, int *slot) {
+    *slot = -1;
+    if (!h->profiling || h->ev_used >= 8192) return 0;
+    if (h->ev_used == h->ev_pool.size()) {
+        EventPair p;
+        CU(cudaEventCreate(&p.a));
+        CU(cudaEventCreate(&p.b));
+        h->ev_pool.push_back(p);
+    }
+    *slot = (int)h->ev_used++;
+    h->ev_pool[*slot].kind = kind;
+    CU(cudaEventRecord(h->ev_pool[*slot].a, h->stream));
+    return 0;
+}
+int ev_end(lda_b200_handle *h, int slot) {
+    if (slot >= 0) CU(cudaEventRecord(h->ev_pool[slot].b, h->stream));
+    return 0;
+}
+int ev_collect(lda_b200_handle *h) {
+    h->mb_ms = h->blend_ms = 0;
+    h->mb_n = h->blend_n = 0;
+    for (size_t i = 0; i < h->ev_used; ++i) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b));
+        if (h->ev_pool[i].kind == 0) {
+            h->mb_ms += ms;
+            h->mb_n++;
+        } else {
+            h->blend_ms += ms;
+            h->blend_n++;
+        }
+    }
+    h->ev_used = 0;
+    return 0;
+}
+
+// ---- model allocation -------------------------------------------------------------------------------
+int ensure_model(lda_b200_handle *h, int64_t W) {
+    const int K = h->cfg.K, Kp = (K + 3) & ~3;
+    if (h->W == W && h->K == K && h->nphi) return 0;
+    if (W < 1) return fail(h, LDA_B200_EINVAL, "matrix has no rows (W = %lld)", (long long)W);
+    if (W > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "W = %lld exceeds int32 word ids", (long long)W);
+    h->W = W;
+    h->K = K;
+    h->Kp = Kp;
+    h->fitted = false;
+    TRY(dalloc(h, &h->nphi, (size_t)W * Kp));
+    TRY(dalloc(h, &h->nphi_hat, (size_t)W * Kp));
+    TRY(dalloc(h, &h->nz, (size_t)Kp));
+    TRY(dalloc(h, &h->nzhat, (size_t)Kp));
+    TRY(dalloc(h, &h->colsum, (size_t)Kp));
+    TRY(dalloc(h, &h->inv_z, (size_t)Kp));
+    TRY(dalloc(h, &h->inv_colsum, (size_t)Kp));
+    CU(cudaMemsetAsync(h->nphi_hat, 0, (size_t)W * Kp * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->nzhat, 0, (size_t)Kp * sizeof(double), h->stream));
+    CU(cudaMemsetAsync(h->nz, 0, (size_t)Kp * sizeof(double), h->stream));
+    return 0;
+}
+
+int ensure_rho_table(lda_b200_handle *h, int n) {
+    if (n <= h->rho_cap) return 0;
+    TRY(dalloc(h, &h->rho_tab, (size_t)n));
+    h->rho_cap = n;
+    return 0;
+}
+
+int fill_rho_table(lda_b200_handle *h, double t0, int n) {
+    TRY(ensure_rho_table(h, n));
+    const lda_b200_schedule &s = h->cfg.rho_theta;
+    rho_table_kernel<<<(n + 127) / 128, 128, 0, h->stream>>>(s.S, s.Tau, s.Kappa, t0, n, h->rho_tab);
+    KCHECK();
+    return 0;
+}
+
+// nZ[k] = sum_i nPhi[i,k] (lda.go:203) and invZ
+int refresh_nz_from_nphi(lda_b200_handle *h) {
+    CU(cudaMemsetAsync(h->nz, 0, (size_t)h->Kp * sizeof(double), h->stream));
+    const int bs = blend_block(h->Kp);
+    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->nz);
+    KCHECK();
+    return 0;
+}
+int refresh_inv_z(lda_b200_handle *h) {
+    inv_z_kernel<<<(h->Kp + 127) / 128, 128, 0, h->stream>>>(h->nz, h->inv_z, h->K, h->Kp, h->cfg.eta * (double)h->W);
+    KCHECK();
+    return 0;
+}
+
+// ---- host -> device ingestion -----------------------------------------------------------------------
+std::vector<Segment> make_segments(int64_t D, int64_t b, int rank, int R) {
+    std::vector<Segment> s;
+    if (R <= 1) {
+        s.push_back({0, D, 0});
+        return s;
+    }
+    const int64_t M = (D + b - 1) / b;
+    int64_t l0 = 0;
+    for (int64_t m = rank; m < M; m += R) {
+        const int64_t g0 = m * b, g1 = std::min(D, g0 + b);
+        s.push_back({g0, g1, l0});
+        l0 += g1 - g0;
+    }
+    return s;
+}
+
+// copies [R][K] float64 host rows of the given segments into [Dl][Kp] fp32 device rows
+int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const double *src, int K, int Kp, float *dst) {
+    const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / sizeof(double)) / K);
+    for (const Segment &s : segs) {
+        for (int64_t g = s.g0; g < s.g1; g += rows_per_chunk) {
+            const int64_t n = std::min(rows_per_chunk, s.g1 - g);
+            CU(cudaMemcpyAsync(h->stage, src + g * K, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            pad_rows_kernel<<<grid_for(n * Kp, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage,
+                                                                                    dst + (s.l0 + (g - s.g0)) * Kp, n, K, Kp);
+            KCHECK();
+        }
+    }
+    return 0;
+}
+
+// Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
+int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                  const double *data, double *wc64_out /*device, optional*/) {
+    if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
+    if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
+    free_corpus(c);
+    c.D = D;
+    c.b = h->cfg.batch_size;
+    c.segs = make_segments(D, c.b, h->rank, h->nranks);
+    int64_t Dl = 0;
+    for (const Segment &s : c.segs) Dl += s.g1 - s.g0;
+    c.Dl = Dl;
+    if (Dl > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "more than 2^31 documents per GPU");
+
+    std::vector<int64_t> lp((size_t)Dl + 1);
+    lp[0] = 0;
+    for (const Segment &s : c.segs) {
+        for (int64_t g = s.g0; g < s.g1; ++g) {
+            const int64_t n = indptr[g + 1] - indptr[g];
+            if (n < 0 || indptr[g] < 0) return fail(h, LDA_B200_EINVAL, "indptr is not non-decreasing at column %lld", (long long)g);
+            if (n > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "document %lld has more than 2^31 entries", (long long)g);
+            const int64_t l = s.l0 + (g - s.g0);
+            lp[l + 1] = lp[l] + n;
+        }
+    }
+    c.nnz = lp[Dl];
+    if (c.nnz > 0 && (!ind || !data)) return fail(h, LDA_B200_EINVAL, "ind/data is NULL");
+    TRY(dalloc(h, &c.doc_ptr, (size_t)Dl + 1));
+    TRY(dalloc(h, &c.ind, (size_t)c.nnz));
+    TRY(dalloc(h, &c.val, (size_t)c.nnz));
+    TRY(dalloc(h, &c.wc, (size_t)Dl));
+    CU(cudaMemcpyAsync(c.doc_ptr, lp.data(), ((size_t)Dl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+
+    const int64_t chunk = (int64_t)(h->stage_bytes / 8);
+    for (const Segment &s : c.segs) {
+        const int64_t p0 = indptr[s.g0], p1 = indptr[s.g1];
+        const int64_t l0 = lp[s.l0];
+        for (int64_t p = p0; p < p1; p += chunk) {
+            const int64_t n = std::min(chunk, p1 - p);
+            CU(cudaMemcpyAsync(h->stage, ind + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, c.ind + l0 + (p - p0), n,
+                                                                                  W, h->err_flag);
+            KCHECK();
+            CU(cudaMemcpyAsync(h->stage, data + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage, c.val + l0 + (p - p0), n);
+            KCHECK();
+        }
+    }
+    CU(cudaMemsetAsync(h->dacc + 1, 0, sizeof(double), h->stream));
+    if (Dl > 0) {
+        doc_wc_kernel<<<grid_for(Dl * 32, 256, h->sms * 8), 256, 0, h->stream>>>(c.doc_ptr, c.val, (int)Dl, c.wc, wc64_out, h->dacc + 1);
+        KCHECK();
+    }
+    if (h->nranks > 1) NC(nccl().AllReduce(h->dacc + 1, h->dacc + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    CU(cudaMemcpyAsync(h->h_pinned, h->dacc + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(h->h_pinned + 1, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    c.n_global = h->h_pinned[0];
+    int bad;
+    memcpy(&bad, h->h_pinned + 1, sizeof(int));
+    if (bad) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)W);
+    return 0;
+}
+
+// initial nTheta / theta (lda.go:472-475, 422-426): either caller-provided values or PCG draws on the device
+int init_theta(lda_b200_handle *h, Corpus &c, const double *theta0, lda_b200_pcg *rnd, uint64_t first_draw) {
+    TRY(dalloc(h, &c.theta, (size_t)c.Dl * h->Kp));
+    if (theta0) return upload_rows(h, c.segs, theta0, h->K, h->Kp, c.theta);
+    if (!rnd) return fail(h, LDA_B200_EINVAL, "neither initial values nor a PCG state were given");
+    if (c.Dl > 0) {
+        const int64_t work = c.Dl * ((h->K + PCG_CH - 1) / PCG_CH);
+        pcg_fill_rows_kernel<<<grid_for(work, 128, h->sms * 16), 128, 0, h->stream>>>(
+            rnd->high, rnd->low, first_draw, (uint64_t)c.D * (uint64_t)h->K, c.Dl, h->K, h->Kp, c.b, h->nranks, h->rank, c.theta);
+        KCHECK();
+    }
+    return 0;
+}
+
+void advance(lda_b200_pcg *rnd, uint64_t draws) {
+    Pcg p;
+    p.s = mk128(rnd->high, rnd->low);
+    pcg_jump(p, draws);
+    rnd->high = (uint64_t)(p.s >> 64);
+    rnd->low = (uint64_t)p.s;
+}
+
+// perplexity (lda.go:392-408) of the corpus under theta and the current nPhi, with denominator `sum`
+int eval_perplexity(lda_b200_handle *h, const Corpus &c, double sum, double *out) {
+    CU(cudaMemsetAsync(h->colsum, 0, (size_t)h->Kp * sizeof(double), h->stream));
+    const int bs = blend_block(h->Kp);
+    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->colsum);
+    KCHECK();
+    reciprocal_kernel<<<(h->Kp + 127) / 128, 128, 0, h->stream>>>(h->colsum, h->inv_colsum, h->K, h->Kp);
+    KCHECK();
+    CU(cudaMemsetAsync(h->dacc, 0, sizeof(double), h->stream));
+    PerpArgs a;
+    a.doc_ptr = c.doc_ptr;
+    a.ind = c.ind;
+    a.val = c.val;
+    a.theta = c.theta;
+    a.nphi = h->nphi;
+    a.inv_colsum = h->inv_colsum;
+    a.acc = h->dacc;
+    a.n_docs = (int)c.Dl;
+    a.Kp = h->Kp;
+    TRY(launch_perplexity(h, a));
+    if (h->nranks > 1) NC(nccl().AllReduce(h->dacc, h->dacc, 1, ncclDouble, ncclSum, h->comm, h->stream));
+    CU(cudaMemcpyAsync(h->h_pinned, h->dacc, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = exp2(-h->h_pinned[0] / sum);
+    return 0;
+}
+
+// normaliseTheta + transposed float64 copy (lda.go:452, 541) into the caller's K x D matrix
+int write_theta_out(lda_b200_handle *h, const Corpus &c, double *theta_out) {
+    if (!theta_out || c.Dl == 0) return 0;
+    double *dout = nullptr;
+    TRY(dalloc(h, &dout, (size_t)h->K * c.Dl));
+    transpose_out_kernel<true><<<(unsigned)((c.Dl + 31) / 32), 256, 0, h->stream>>>(c.theta, c.Dl, h->K, h->Kp, nullptr, dout, c.Dl);
+    h->launches++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) {
+        for (const Segment &s : c.segs) {
+            e = cudaMemcpy2DAsync(theta_out + s.g0, (size_t)c.D * sizeof(double), dout + s.l0, (size_t)c.Dl * sizeof(double),
+                                  (size_t)(s.g1 - s.g0) * sizeof(double), (size_t)h->K, cudaMemcpyDeviceToHost, h->stream);
+            if (e != cudaSuccess) break;
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, LDA_B200_ECUDA, "theta read-back failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
+    DocsArgs a;
+    a.doc_ptr = c.doc_ptr;
+    a.ind = c.ind;
+    a.val = c.val;
+    a.wc = c.wc;
+    a.theta = c.theta;
+    a.nphi = h->nphi;
+    a.nphi_hat = h->nphi_hat;
+    a.inv_z = h->inv_z;
+    a.log1m_rho = h->rho_tab;
+    a.passes_out = nullptr;
+    a.doc_counter = h->doc_counter;
+    a.doc_begin = 0;
+    a.doc_end = (int)c.Dl;
+    a.K = h->K;
+    a.Kp = h->Kp;
+    a.passes = passes;
+    a.change_freq = h->cfg.change_evaluation_frequency;
+    a.change_tol = (float)h->cfg.mean_change_tolerance;
+    a.alpha = (float)h->cfg.alpha;
+    a.eta = (float)h->cfg.eta;
+    a.hat_scale = 0.f;
+    return a;
+}
+
+inline double rho_calc(const lda_b200_schedule &s, double t) { return s.S / pow(s.Tau + t, s.Kappa); }  // lda.go:30-32
+
+// unNormalisedTransform (lda.go:420-437) on an uploaded corpus
+int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, int32_t *passes_out_host) {
+    const int T = h->cfg.transformation_passes;
+    TRY(fill_rho_table(h, rho_theta_t, T + 1));
+    int32_t *dpass = nullptr;
+    if (passes_out_host) TRY(dalloc(h, &dpass, (size_t)c.Dl));
+    CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
+    DocsArgs a = docs_args(h, c, T);
+    a.passes_out = dpass;
+    int rc = launch_docs<false>(h, a);
+    if (!rc && passes_out_host) {
+        std::vector<int32_t> tmp((size_t)c.Dl);
+        cudaError_t e = cudaMemcpyAsync(tmp.data(), dpass, (size_t)c.Dl * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "passes read-back failed: %s", cudaGetErrorString(e));
+        for (const Segment &s : c.segs)
+            for (int64_t g = s.g0; g < s.g1 && !rc; ++g) passes_out_host[g] = tmp[(size_t)(s.l0 + g - s.g0)];
+    }
+    if (dpass) cudaFree(dpass);
+    return rc;
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+void lda_b200_default_config(int32_t k, lda_b200_config *c) {
+    if (!c) return;
+    c->K = k;
+    c->iterations = 1000;
+    c->batch_size = 100;
+    c->burn_in_passes = 1;
+    c->transformation_passes = 500;
+    c->perplexity_evaluation_frequency = 30;
+    c->change_evaluation_frequency = 30;
+    c->processes = 1;
+    c->perplexity_tolerance = 1e-2;
+    c->mean_change_tolerance = 1e-5;
+    c->alpha = 0.1;
+    c->eta = 0.01;
+    c->rho_phi = {10, 1000, 0.9};
+    c->rho_theta = {1, 10, 0.9};
+}
+
+const char *lda_b200_last_error(const lda_b200_handle *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle **out) {
+    lda_b200_handle *h = nullptr;
+    if (!out) return fail(h, LDA_B200_EINVAL, "out is NULL");
+    *out = nullptr;
+    TRY(validate_config(h, cfg));
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(h, LDA_B200_ECUDA, "no CUDA device available (%s); liblda_b200 has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(h, LDA_B200_EINVAL, "device %d out of range [0,%d)", device, ndev);
+    lda_b200_handle *nh = new lda_b200_handle();
+    nh->cfg = *cfg;
+    nh->device = device;
+    auto init = [&](lda_b200_handle *h) -> int {
+        CU(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        h->sms = prop.multiProcessorCount;
+        CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        TRY(dalloc(h, &h->ticket, 1));
+        TRY(dalloc(h, &h->doc_counter, 1));
+        TRY(dalloc(h, &h->err_flag, 1));
+        TRY(dalloc(h, &h->dacc, 2));
+        CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
+        CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
+        h->stage_bytes = (size_t)256 << 20;
+        CU(cudaMalloc(&h->stage, h->stage_bytes));
+        CU(cudaMallocHost((void **)&h->h_pinned, 64));
+        return 0;
+    };
+    int rc = init(nh);
+    if (rc) {
+        g_create_error = nh->err;
+        lda_b200_destroy(nh);
+        return rc;
+    }
+    *out = nh;
+    return 0;
+}
+
+void lda_b200_destroy(lda_b200_handle *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) nccl().CommDestroy(h->comm);
+    free_corpus(h->fitc);
+    dfree(&h->nphi);
+    dfree(&h->nphi_hat);
+    dfree(&h->nz);
+    dfree(&h->nzhat);
+    dfree(&h->colsum);
+    dfree(&h->inv_z);
+    dfree(&h->inv_colsum);
+    dfree(&h->ticket);
+    dfree(&h->doc_counter);
+    dfree(&h->err_flag);
+    dfree(&h->dacc);
+    dfree(&h->rho_tab);
+    if (h->stage) cudaFree(h->stage);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    for (EventPair &p : h->ev_pool) {
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg) {
+    if (!h) return LDA_B200_EINVAL;
+    TRY(validate_config(h, cfg));
+    if (h->fit_open && cfg->K != h->cfg.K) return fail(h, LDA_B200_EINVAL, "K cannot change during a fit");
+    h->cfg = *cfg;
+    return 0;
+}
+
+int lda_b200_set_profiling(lda_b200_handle *h, int32_t on) {
+    if (!h) return LDA_B200_EINVAL;
+    h->profiling = on != 0;
+    return 0;
+}
+
+int lda_b200_comm_unique_id(void *id128) {
+    lda_b200_handle *h = nullptr;
+    if (!id128) return fail(h, LDA_B200_EINVAL, "id buffer is NULL");
+    if (!nccl().load()) return fail(h, LDA_B200_ENCCL, "%s", nccl().load_error);
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    ncclUniqueId id;
+    NC(nccl().GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const void *id128) {
+    if (!h) return LDA_B200_EINVAL;
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, LDA_B200_EINVAL, "bad rank %d of %d", rank, nranks);
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    CU(cudaSetDevice(h->device));
+    if (h->comm) {
+        nccl().CommDestroy(h->comm);
+        h->comm = nullptr;
+    }
+    h->rank = 0;
+    h->nranks = 1;
+    if (nranks == 1) return 0;
+    if (!id128) return fail(h, LDA_B200_EINVAL, "id is NULL");
+    if (!nccl().load()) return fail(h, LDA_B200_ENCCL, "%s", nccl().load_error);
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    NC(nccl().CommInitRank(&h->comm, nranks, id, rank));
+    h->rank = rank;
+    h->nranks = nranks;
+    return 0;
+}
+
+// ---- FitTransform, lda.go:463-542 ----------------------------------------------------------------------
+int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                       const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                       lda_b200_counters *ctr) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
+    if ((!nphi0 || !ntheta0) && !rnd) return fail(h, LDA_B200_EINVAL, "neither initial values nor a PCG state were given");
+    CU(cudaSetDevice(h->device));
+    h->fit_open = false;
+    // init (lda.go:193-206): nPhi/nZ are re-allocated on every fit, no warm start
+    h->W = 0;
+    TRY(ensure_model(h, W));
+    uint64_t draws = 0;
+    if (nphi0) {
+        std::vector<Segment> all{{0, W, 0}};
+        TRY(upload_rows(h, all, nphi0, h->K, h->Kp, h->nphi));
+    } else {
+        const int64_t work = W * ((h->K + PCG_CH - 1) / PCG_CH);
+        pcg_fill_rows_kernel<<<grid_for(work, 128, h->sms * 16), 128, 0, h->stream>>>(rnd->high, rnd->low, 0, (uint64_t)W * (uint64_t)h->K,
+                                                                                  W, h->K, h->Kp, W, 1, 0, h->nphi);
+        KCHECK();
+        draws += (uint64_t)W * (uint64_t)h->K;
+    }
+    TRY(refresh_nz_from_nphi(h));
+    TRY(refresh_inv_z(h));
+
+    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr));
+    TRY(init_theta(h, h->fitc, ntheta0, rnd, draws));
+    if (!ntheta0) draws += (uint64_t)D * (uint64_t)h->K;
+    if (rnd && draws) advance(rnd, draws);
+
+    ctr->words_in_corpus += h->fitc.n_global;  // lda.go:481 (never reset)
+    ctr->rho_phi_t = 1;                        // lda.go:497
+    CU(cudaMemsetAsync(h->nphi_hat, 0, (size_t)h->W * h->Kp * sizeof(float), h->stream));
+    CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
+    h->it_done = 0;
+    h->prev_perplexity = 0;
+    h->stopped = false;
+    h->fit_open = true;
+    h->fitted = true;
+    return 0;
+}
+
+int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_counters *ctr, double *perp_trace,
+                         int32_t perp_cap, int32_t *n_evals, int32_t *iters_run, int32_t *stopped, float *elapsed_ms) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fit_open) return fail(h, LDA_B200_ESTATE, "lda_b200_fit_iterate without lda_b200_fit_begin");
+    if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
+    CU(cudaSetDevice(h->device));
+    const Corpus &c = h->fitc;
+    const lda_b200_config &cfg = h->cfg;
+    const int R = h->nranks;
+    const int64_t b = c.b;
+    const int64_t M = (c.D + b - 1) / b;      // numMiniBatches, lda.go:487
+    const int64_t nsteps = (M + R - 1) / R;
+    const int B = cfg.burn_in_passes;
+    int evals = 0, ran = 0;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (elapsed_ms) {
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        CU(cudaEventRecord(e0, h->stream));
+    }
+    h->ev_used = 0;
+
+    for (int it = 0; it < n_iterations && !h->stopped && h->it_done < cfg.iterations; ++it) {
+        ctr->rho_theta_t += 1;  // lda.go:502
+        TRY(fill_rho_table(h, ctr->rho_theta_t, B + 1));
+        for (int64_t s = 0; s < nsteps; ++s) {
+            const int n_s = (int)std::min<int64_t>(R, M - s * R);  // minibatches processed in this step
+            // Eqn 7/8 for n_s minibatches blended one after the other (lda.go:299-317), each computed from the
+            // same nPhi snapshot: nPhi' = A nPhi + sum_g c_g nPhiHat_g
+            double A = 1.0, cg = 0.0;
+            {
+                double tail = 1.0;
+                for (int g = n_s - 1; g >= 0; --g) {
+                    const double rho = rho_calc(cfg.rho_phi, ctr->rho_phi_t + g);
+                    if (g == h->rank) cg = rho * tail;
+                    tail *= (1.0 - rho);
+                }
+                A = tail;
+            }
+            if (h->rank < n_s) {
+                const int64_t m = s * R + h->rank;
+                const int64_t b_actual = (m < M - 1) ? b : c.D - m * b;  // lda.go:513-518, :268
+                DocsArgs a = docs_args(h, c, B);
+                a.doc_begin = (int)(s * b);
+                a.doc_end = (int)(s * b + b_actual);
+                a.hat_scale = (float)(ctr->words_in_corpus / (double)b_actual * (R > 1 ? cg : 1.0));
+                int slot;
+                TRY(ev_begin(h, 0, &slot));
+                TRY(launch_docs<true>(h, a));
+                TRY(ev_end(h, slot));
+            }
+            if (R > 1)
+                NC(nccl().AllReduce(h->nphi_hat, h->nphi_hat, (size_t)h->W * h->Kp, ncclFloat, ncclSum, h->comm, h->stream));
+            BlendArgs ba;
+            ba.nphi = h->nphi;
+            ba.nphi_hat = h->nphi_hat;
+            ba.nz = h->nz;
+            ba.nzhat = h->nzhat;
+            ba.inv_z = h->inv_z;
+            ba.ticket = h->ticket;
+            ba.doc_counter = h->doc_counter;
+            ba.W = h->W;
+            ba.K = h->K;
+            ba.Kp = h->Kp;
+            ba.Ad = A;
+            ba.Cd = (R > 1) ? 1.0 : cg;
+            ba.A = (float)ba.Ad;
+            ba.C = (float)ba.Cd;
+            ba.etaW = cfg.eta * (double)h->W;
+            const int bs = blend_block(h->Kp);
+            int slot;
+            TRY(ev_begin(h, 1, &slot));
+            phi_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(ba);
+            KCHECK();
+            TRY(ev_end(h, slot));
+            ctr->rho_phi_t += n_s;  // lda.go:300
+        }
+        h->it_done++;
+        ran++;
+        const int f = cfg.perplexity_evaluation_frequency;
+        if (f > 0 && h->it_done % f == 0) {  // lda.go:530-539
+            double p;
+            TRY(eval_perplexity(h, c, ctr->words_in_corpus, &p));
+            if (perp_trace && evals < perp_cap) perp_trace[evals] = p;
+            evals++;
+            if (h->prev_perplexity != 0 && fabs(h->prev_perplexity - p) < cfg.perplexity_tolerance) {
+                h->stopped = true;
+                break;
+            }
+            h->prev_perplexity = p;
+        }
+    }
+    if (elapsed_ms) {
+        CU(cudaEventRecord(e1, h->stream));
+        CU(cudaEventSynchronize(e1));
+        CU(cudaEventElapsedTime(elapsed_ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    } else {
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    if (h->profiling) TRY(ev_collect(h));
+    if (n_evals) *n_evals = evals;
+    if (iters_run) *iters_run = ran;
+    if (stopped) *stopped = h->stopped ? 1 : 0;
+    return 0;
+}
+
+int lda_b200_fit_end(lda_b200_handle *h, double *theta_out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fit_open) return fail(h, LDA_B200_ESTATE, "lda_b200_fit_end without lda_b200_fit_begin");
+    CU(cudaSetDevice(h->device));
+    int rc = write_theta_out(h, h->fitc, theta_out);
+    free_corpus(h->fitc);
+    h->fit_open = false;
+    return rc;
+}
+
+int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                 const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                 lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
+                 int32_t *iters_run) {
+    if (!h) return LDA_B200_EINVAL;
+    TRY(lda_b200_fit_begin(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr));
+    int rc = lda_b200_fit_iterate(h, h->cfg.iterations, ctr, perp_trace, perp_cap, n_evals, iters_run, nullptr, nullptr);
+    if (rc) {
+        free_corpus(h->fitc);
+        h->fit_open = false;
+        return rc;
+    }
+    return lda_b200_fit_end(h, theta_out);
+}
+
+// ---- Transform / Perplexity / Components -----------------------------------------------------------------
+int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                       const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *theta_out,
+                       int32_t *passes_out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Transform called before Fit / set_state");
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    CU(cudaSetDevice(h->device));
+    Corpus c;
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr);
+    if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
+    if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
+    if (!rc) rc = run_transform(h, c, rho_theta_t, passes_out);
+    if (!rc) rc = write_theta_out(h, c, theta_out);
+    if (!rc) {
+        cudaError_t e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "transform failed: %s", cudaGetErrorString(e));
+    }
+    free_corpus(c);
+    return rc;
+}
+
+int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                        const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!out) return fail(h, LDA_B200_EINVAL, "out is NULL");
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Perplexity called before Fit / set_state");
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    CU(cudaSetDevice(h->device));
+    Corpus c;
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr);  // wordCount = c.n_global, lda.go:372-385
+    if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
+    if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
+    if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr);
+    if (!rc) rc = eval_perplexity(h, c, c.n_global, out);
+    free_corpus(c);
+    return rc;
+}
+
+int lda_b200_components(lda_b200_handle *h, double *out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!out) return fail(h, LDA_B200_EINVAL, "out is NULL");
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Components called before Fit / set_state");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemsetAsync(h->colsum, 0, (size_t)h->Kp * sizeof(double), h->stream));
+    const int bs = blend_block(h->Kp);
+    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->colsum);
+    KCHECK();
+    double *dout = nullptr;
+    TRY(dalloc(h, &dout, (size_t)h->K * h->W));
+    transpose_out_kernel<false><<<(unsigned)((h->W + 31) / 32), 256, 0, h->stream>>>(h->nphi, h->W, h->K, h->Kp, h->colsum, dout, h->W);
+    h->launches++;
+    cudaError_t e = cudaPeekAtLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)h->K * h->W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dout);
+    if (e != cudaSuccess) return fail(h, LDA_B200_ECUDA, "components failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int lda_b200_get_dims(const lda_b200_handle *h, int64_t *W, int32_t *K) {
+    if (!h) return LDA_B200_EINVAL;
+    if (W) *W = h->W;
+    if (K) *K = h->cfg.K;
+    return 0;
+}
+
+int lda_b200_get_state(lda_b200_handle *h, double *nphi, double *nz) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "no model state");
+    CU(cudaSetDevice(h->device));
+    if (nphi) {
+        const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / sizeof(double)) / h->K);
+        for (int64_t r = 0; r < h->W; r += rows_per_chunk) {
+            const int64_t n = std::min(rows_per_chunk, h->W - r);
+            unpad_rows_kernel<<<grid_for(n * h->K, 256, h->sms * 8), 256, 0, h->stream>>>(h->nphi + r * h->Kp, (double *)h->stage, n, h->K, h->Kp);
+            KCHECK();
+            CU(cudaMemcpyAsync(nphi + r * h->K, h->stage, (size_t)n * h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+        }
+    }
+    if (nz) {
+        CU(cudaMemcpyAsync(nz, h->nz, (size_t)h->K * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
+    return 0;
+}
+
+int lda_b200_set_state(lda_b200_handle *h, int64_t W, const double *nphi, const double *nz) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!nphi || !nz) return fail(h, LDA_B200_EINVAL, "nphi/nz is NULL");
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    CU(cudaSetDevice(h->device));
+    h->W = 0;
+    TRY(ensure_model(h, W));
+    std::vector<Segment> all{{0, W, 0}};
+    TRY(upload_rows(h, all, nphi, h->K, h->Kp, h->nphi));
+    CU(cudaMemsetAsync(h->nz, 0, (size_t)h->Kp * sizeof(double), h->stream));
+    CU(cudaMemcpyAsync(h->nz, nz, (size_t)h->K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    TRY(refresh_inv_z(h));
+    CU(cudaStreamSynchronize(h->stream));
+    h->fitted = true;
+    return 0;
+}
+
+// ---- PCG host helpers ------------------------------------------------------------------------------------
+void lda_b200_pcg_seed(lda_b200_pcg *rnd, uint64_t seed) {
+    rnd->high = seed;
+    rnd->low = seed;
+}
+uint64_t lda_b200_pcg_uint64(lda_b200_pcg *rnd) {
+    Pcg p;
+    p.s = mk128(rnd->high, rnd->low);
+    const uint64_t r = pcg_next(p);
+    rnd->high = (uint64_t)(p.s >> 64);
+    rnd->low = (uint64_t)p.s;
+    return r;
+}
+void lda_b200_pcg_fill(lda_b200_pcg *rnd, int64_t count, int64_t n, double *out) {
+    Pcg p;
+    p.s = mk128(rnd->high, rnd->low);
+    for (int64_t i = 0; i < count; ++i) out[i] = pcg_draw(p, (uint64_t)n);
+    rnd->high = (uint64_t)(p.s >> 64);
+    rnd->low = (uint64_t)p.s;
+}
+void lda_b200_pcg_advance(lda_b200_pcg *rnd, uint64_t draws) { advance(rnd, draws); }
+
+// ---- diagnostics -------------------------------------------------------------------------------------------
+int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                              const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
+                              double *wc_out, double *n_out) {
+    if (!h) return LDA_B200_EINVAL;
+    CU(cudaSetDevice(h->device));
+    Corpus c;
+    double *wc64 = nullptr;
+    int rc = dalloc(h, &wc64, (size_t)std::max<int64_t>(D, 1));
+    if (!rc) rc = upload_corpus(h, c, W, D, indptr, ind, data, wc64);
+    auto back = [&]() -> int {
+        if (indptr_out) CU(cudaMemcpyAsync(indptr_out, c.doc_ptr, (size_t)(c.Dl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        if (ind_out) CU(cudaMemcpyAsync(ind_out, c.ind, (size_t)c.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        if (val_out) CU(cudaMemcpyAsync(val_out, c.val, (size_t)c.nnz * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        if (wc_out) CU(cudaMemcpyAsync(wc_out, wc64, (size_t)c.Dl * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (n_out) *n_out = c.n_global;
+        return 0;
+    };
+    if (!rc) rc = back();
+    free_corpus(c);
+    if (wc64) cudaFree(wc64);
+    return rc;
+}
+
+int64_t lda_b200_launch_count(const lda_b200_handle *h) { return h ? h->launches : 0; }
+
+int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
+                              float *blend_ms, int32_t *blend_launches) {
+    if (!h) return LDA_B200_EINVAL;
+    if (minibatch_ms) *minibatch_ms = h->mb_ms;
+    if (minibatch_launches) *minibatch_launches = h->mb_n;
+    if (blend_ms) *blend_ms = h->blend_ms;
+    if (blend_launches) *blend_launches = h->blend_n;
+    return 0;
+}
+
+}  // extern "C"

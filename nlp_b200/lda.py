@@ -1,0 +1,312 @@
+"""Host-side mirror of `nlp.LatentDirichletAllocation` (reference lda.go:60-542) over the C ABI of liblda_b200.so.
+
+Same exported field names, constructor defaults (lda.go:160-186), method names and result orientation as the Go
+type, so that parity tests read like lda_test.go.  All arithmetic of the path runs in CUDA kernels; this file only
+marshals arguments (the Go shim in INTEGRATION.md does the same through cgo).
+"""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib, rand
+
+# term x document matrix in compressed-sparse-column form: what sparse.CSC holds after ToCSC() (lda.go:464-466)
+CSC = namedtuple("CSC", "rows cols indptr ind data")
+
+
+class LearningSchedule:
+    """lda.go:16-32"""
+
+    def __init__(self, S, Tau, Kappa):
+        self.S, self.Tau, self.Kappa = float(S), float(Tau), float(Kappa)
+
+    def Calc(self, iteration):
+        return self.S / (self.Tau + iteration) ** self.Kappa
+
+    def _c(self):
+        return _lib.Schedule(self.S, self.Tau, self.Kappa)
+
+
+def as_csc(m):
+    """ToCSC() / ColNonZeroElemDo semantics (lda.go:464-466, utils.go:45-59).
+
+    sparse input: converted to CSC (rows ascending inside a column; an input that already is CSC keeps its stored
+    order); dense input: every column lists its non-zero rows in ascending order, exact zeros skipped."""
+    if isinstance(m, CSC):
+        rows, cols, indptr, ind, data = m
+    elif hasattr(m, "tocsc"):
+        s = m if getattr(m, "format", None) == "csc" else m.tocsc()
+        rows, cols = s.shape
+        indptr, ind, data = s.indptr, s.indices, s.data
+    else:
+        a = np.asarray(m, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("nlp: matrix must be 2-dimensional")
+        rows, cols = a.shape
+        at = a.T
+        jj, ii = np.nonzero(at)
+        indptr = np.concatenate(([0], np.cumsum(np.bincount(jj, minlength=cols)))) if cols else np.zeros(1)
+        ind, data = ii, at[jj, ii]
+    return CSC(int(rows), int(cols), np.ascontiguousarray(indptr, dtype=np.int64),
+               np.ascontiguousarray(ind, dtype=np.int64), np.ascontiguousarray(data, dtype=np.float64))
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class LatentDirichletAllocation:
+    """lda.go:68-141.  Use NewLatentDirichletAllocation(k)."""
+
+    def __init__(self, k, device=0):
+        # defaults: lda.go:160-186
+        self.Iterations = 1000
+        self.PerplexityTolerance = 1e-2
+        self.PerplexityEvaluationFrequency = 30
+        self.BatchSize = 100
+        self.K = int(k)
+        self.BurnInPasses = 1
+        self.TransformationPasses = 500
+        self.MeanChangeTolerance = 1e-5
+        self.ChangeEvaluationFrequency = 30
+        self.Alpha = 0.1
+        self.Eta = 0.01
+        self.RhoPhi = LearningSchedule(10, 1000, 0.9)
+        self.RhoTheta = LearningSchedule(1, 10, 0.9)
+        self.rhoPhiT = 1.0
+        self.rhoThetaT = 1.0
+        self.wordsInCorpus = 0.0
+        self.w = self.d = 0
+        import time
+        self.Rnd = rand.New(rand.NewSource(time.time_ns() & 0xFFFFFFFFFFFFFFFF))
+        # Processes (lda.go:134) = number of minibatches in flight = number of GPUs = torch.distributed world size
+        self.Processes = _world()[1]
+        # --- not in the reference ---
+        self.Device = device
+        self.DeviceInit = True       # draw the initial nPhi / nTheta from Rnd on the GPU (bit-identical stream)
+        self.PerplexityTrace = []    # perplexities evaluated inside the last fit (lda.go:530-539 hides them)
+        self.IterationsRun = 0
+        self._h = None
+        self._comm_ranks = 1
+
+    # ---- handle management ------------------------------------------------------------------------------
+    def _config(self):
+        c = _lib.Config()
+        c.K = self.K
+        c.iterations = self.Iterations
+        c.batch_size = self.BatchSize
+        c.burn_in_passes = self.BurnInPasses
+        c.transformation_passes = self.TransformationPasses
+        c.perplexity_evaluation_frequency = self.PerplexityEvaluationFrequency
+        c.change_evaluation_frequency = self.ChangeEvaluationFrequency
+        c.processes = self.Processes
+        c.perplexity_tolerance = self.PerplexityTolerance
+        c.mean_change_tolerance = self.MeanChangeTolerance
+        c.alpha, c.eta = self.Alpha, self.Eta
+        c.rho_phi, c.rho_theta = self.RhoPhi._c(), self.RhoTheta._c()
+        return c
+
+    def _handle(self):
+        L = _lib.lib()
+        cfg = self._config()
+        if self._h is None:
+            h = C.c_void_p()
+            _lib.check(L.lda_b200_create(cfg, self.Device, C.byref(h)))
+            self._h = h
+        else:
+            _lib.check(L.lda_b200_set_config(self._h, cfg), self._h)
+        want = max(1, min(self.Processes, _world()[1]))
+        if want != self._comm_ranks:
+            self._init_comm(want)
+        return self._h
+
+    def _init_comm(self, nranks):
+        """one process per GPU: rank 0 creates the ncclUniqueId, torch.distributed carries it to the others"""
+        L = _lib.lib()
+        rank, world = _world()
+        if nranks > 1:
+            import torch
+            import torch.distributed as dist
+            buf = (C.c_ubyte * 128)()
+            if rank == 0:
+                _lib.check(L.lda_b200_comm_unique_id(buf))
+            t = torch.tensor(list(buf), dtype=torch.uint8)
+            if dist.get_backend() == "nccl":
+                t = t.cuda(self.Device)
+            dist.broadcast(t, src=0)
+            raw = bytes(t.cpu().tolist())
+            _lib.check(L.lda_b200_comm_init(self._h, rank, nranks, raw), self._h)
+        else:
+            _lib.check(L.lda_b200_comm_init(self._h, 0, 1, None), self._h)
+        self._comm_ranks = nranks
+
+    def Close(self):
+        if self._h is not None:
+            _lib.lib().lda_b200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+    def _counters(self):
+        return _lib.Counters(self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus)
+
+    def _take(self, ctr):
+        self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus = ctr.rho_phi_t, ctr.rho_theta_t, ctr.words_in_corpus
+
+    def _draws(self, rows, n_draws_mod):
+        """host-side draws (DeviceInit = False): lda.go:199-205 / 472-475 / 422-426"""
+        return self.Rnd.fill_mod(rows * self.K, n_draws_mod)
+
+    # ---- reference API ------------------------------------------------------------------------------------
+    def Fit(self, m):
+        """lda.go:211-214"""
+        self.FitTransform(m, _want_theta=False)
+        return self
+
+    def FitTransform(self, m, _want_theta=True, nphi0=None, ntheta0=None):
+        """lda.go:463-542.  Returns the K x D doc-topic matrix (float64).  nphi0 / ntheta0 (not in the reference)
+        replace the RNG draws with an exported init, e.g. the reference's own, for deterministic parity runs."""
+        csc = as_csc(m)
+        h = self._handle()
+        L = _lib.lib()
+        self.w, self.d = csc.rows, csc.cols
+        if not self.DeviceInit:
+            if nphi0 is None:
+                nphi0 = self._draws(csc.rows, csc.rows * self.K)
+            if ntheta0 is None:
+                ntheta0 = self._draws(csc.cols, csc.cols * self.K)
+        nphi0 = None if nphi0 is None else np.ascontiguousarray(nphi0, dtype=np.float64)
+        ntheta0 = None if ntheta0 is None else np.ascontiguousarray(ntheta0, dtype=np.float64)
+        if nphi0 is not None and nphi0.size != csc.rows * self.K:
+            raise ValueError("nlp: nphi0 must hold W*K values")
+        if ntheta0 is not None and ntheta0.size != csc.cols * self.K:
+            raise ValueError("nlp: ntheta0 must hold D*K values")
+        theta = np.zeros((self.K, csc.cols), dtype=np.float64) if _want_theta else None
+        cap = self.Iterations // self.PerplexityEvaluationFrequency + 1 if self.PerplexityEvaluationFrequency > 0 else 1
+        trace = np.zeros(cap, dtype=np.float64)
+        n_evals, iters = C.c_int32(0), C.c_int32(0)
+        ctr = self._counters()
+        rc = L.lda_b200_fit(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(nphi0),
+                            _ptr(ntheta0), self.Rnd.src._s, ctr, _ptr(theta), _ptr(trace), cap, C.byref(n_evals),
+                            C.byref(iters))
+        _lib.check(rc, h)
+        self._take(ctr)
+        self.PerplexityTrace = trace[:n_evals.value].tolist()
+        self.IterationsRun = iters.value
+        return theta
+
+    # ---- resident-corpus stepping (not in the reference; lda_b200_fit is exactly these three calls) -------------
+    def FitBegin(self, m, nphi0=None, ntheta0=None):
+        """ingest + init of lda.go:464-497; the corpus stays in HBM until FitEnd"""
+        csc = as_csc(m)
+        h = self._handle()
+        self.w, self.d = csc.rows, csc.cols
+        if not self.DeviceInit:
+            nphi0 = self._draws(csc.rows, csc.rows * self.K) if nphi0 is None else nphi0
+            ntheta0 = self._draws(csc.cols, csc.cols * self.K) if ntheta0 is None else ntheta0
+        nphi0 = None if nphi0 is None else np.ascontiguousarray(nphi0, dtype=np.float64)
+        ntheta0 = None if ntheta0 is None else np.ascontiguousarray(ntheta0, dtype=np.float64)
+        ctr = self._counters()
+        rc = _lib.lib().lda_b200_fit_begin(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data),
+                                           _ptr(nphi0), _ptr(ntheta0), self.Rnd.src._s, ctr)
+        _lib.check(rc, h)
+        self._take(ctr)
+        self.PerplexityTrace = []
+        self.IterationsRun = 0
+
+    def FitIterate(self, n):
+        """n more iterations of the loop at lda.go:501-540; returns (iterations run, stopped, device ms)"""
+        h = self._handle()
+        cap = max(1, n)
+        trace = np.zeros(cap, dtype=np.float64)
+        n_evals, iters, stopped, ms = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_float(0)
+        ctr = self._counters()
+        rc = _lib.lib().lda_b200_fit_iterate(h, n, ctr, _ptr(trace), cap, C.byref(n_evals), C.byref(iters),
+                                             C.byref(stopped), C.byref(ms))
+        _lib.check(rc, h)
+        self._take(ctr)
+        self.PerplexityTrace += trace[:n_evals.value].tolist()
+        self.IterationsRun += iters.value
+        return iters.value, bool(stopped.value), ms.value
+
+    def FitEnd(self, want_theta=True):
+        """lda.go:541: normalised, transposed K x D copy; releases the resident corpus"""
+        h = self._handle()
+        theta = np.zeros((self.K, self.d), dtype=np.float64) if want_theta else None
+        _lib.check(_lib.lib().lda_b200_fit_end(h, _ptr(theta)), h)
+        return theta
+
+    def Transform(self, m, theta0=None, return_passes=False):
+        """lda.go:446-453: K x D doc-topic matrix for new documents under the fitted model"""
+        csc = as_csc(m)
+        h = self._handle()
+        if theta0 is None and not self.DeviceInit:
+            theta0 = self._draws(csc.cols, csc.cols * self.K)
+        theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+        theta = np.zeros((self.K, csc.cols), dtype=np.float64)
+        passes = np.zeros(csc.cols, dtype=np.int32) if return_passes else None
+        rc = _lib.lib().lda_b200_transform(h, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(theta0),
+                                           self.Rnd.src._s, self.rhoThetaT, _ptr(theta), _ptr(passes))
+        _lib.check(rc, h)
+        return (theta, passes) if return_passes else theta
+
+    def Perplexity(self, m, theta0=None):
+        """lda.go:368-389"""
+        csc = as_csc(m)
+        h = self._handle()
+        if theta0 is None and not self.DeviceInit:
+            theta0 = self._draws(csc.cols, csc.cols * self.K)
+        theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+        out = C.c_double(0)
+        rc = _lib.lib().lda_b200_perplexity(h, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(theta0),
+                                            self.Rnd.src._s, self.rhoThetaT, C.byref(out))
+        _lib.check(rc, h)
+        return out.value
+
+    def Components(self):
+        """lda.go:414-416: K x W topic-word matrix"""
+        h = self._handle()
+        out = np.zeros((self.K, self.w), dtype=np.float64)
+        _lib.check(_lib.lib().lda_b200_components(h, _ptr(out)), h)
+        return out
+
+    # ---- persistence (TODO in the reference, lda.go:158) ------------------------------------------------------
+    def GetState(self):
+        h = self._handle()
+        nphi = np.zeros((self.w, self.K), dtype=np.float64)
+        nz = np.zeros(self.K, dtype=np.float64)
+        _lib.check(_lib.lib().lda_b200_get_state(h, _ptr(nphi), _ptr(nz)), h)
+        return nphi, nz
+
+    def SetState(self, nphi, nz):
+        nphi = np.ascontiguousarray(nphi, dtype=np.float64)
+        nz = np.ascontiguousarray(nz, dtype=np.float64)
+        if nphi.ndim != 2 or nphi.shape[1] != self.K or nz.shape != (self.K,):
+            raise ValueError("nlp: state must be nPhi[W,K], nZ[K]")
+        h = self._handle()
+        _lib.check(_lib.lib().lda_b200_set_state(h, nphi.shape[0], _ptr(nphi), _ptr(nz)), h)
+        self.w = nphi.shape[0]
+
+
+def NewLatentDirichletAllocation(k, device=None):
+    """lda.go:145"""
+    if device is None:
+        import os
+        device = int(os.environ.get("LOCAL_RANK", "0")) if _world()[1] > 1 else 0
+    return LatentDirichletAllocation(k, device=device)
+
+
+def _world():
+    """(rank, world size) of the torch.distributed job this process belongs to, (0, 1) outside one"""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except ImportError:
+        pass
+    return 0, 1

@@ -23,6 +23,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 /* ------------------------------------------------------------------------------------
  * golang.org/x/exp/rand: rand.New(rand.NewSource(seed)) -> PCGSource (PCG XSL-RR 128/64)
@@ -99,6 +100,13 @@ typedef struct {
     int64_t perpTraceCap, perpTraceLen;
     int64_t iterationsRun;
     int64_t tokenVisits; /* non-zero visits executed by the last Fit/Transform call */
+    double *iterTime;    /* seconds since the start of the iteration loop at the end of each iteration */
+    int64_t iterTimeCap;
+    /* SyncGroup = G > 1 (not in the reference): deterministic restatement of G workers running in lock step --
+     * minibatches sG..sG+G-1 are all computed from the same nPhi/nZ snapshot, then blended one after the other
+     * in index order (lda.go:299-317 G times).  This is the semantics of the G-GPU path; the
+     * reference's own Processes > 1 schedule is racy and not reproducible. */
+    int64_t SyncGroup;
 } oracle_lda;
 
 /* term x document matrix in CSC: column j = document j, rows = word ids, in stored order.
@@ -144,6 +152,7 @@ void oracle_lda_free(oracle_lda *l) {
     free(l->nPhi);
     free(l->nZ);
     free(l->perpTrace);
+    free(l->iterTime);
     pthread_mutex_destroy(&l->phiMutex);
     pthread_mutex_destroy(&l->zMutex);
     free(l);
@@ -228,8 +237,8 @@ static void mini_batch_reset(mini_batch *b, int64_t K, int64_t w) {
     for (int64_t i = 0; i < K; i++) b->nZHat[i] = 0;
 }
 
-/* lda.go:266-318 */
-static void fit_mini_batch(oracle_lda *l, mini_batch *mb, const double *wc, double *nTheta, const oracle_csc *m) {
+/* first half of fitMiniBatch, lda.go:266-298 */
+static void estep_mini_batch(oracle_lda *l, mini_batch *mb, const double *wc, double *nTheta, const oracle_csc *m) {
     int64_t K = l->K;
     int64_t batchSize = mb->end - mb->start;
     for (int64_t j = mb->start; j < mb->end; j++) {
@@ -257,6 +266,11 @@ static void fit_mini_batch(oracle_lda *l, mini_batch *mb, const double *wc, doub
             mb->visits++;
         }
     }
+}
+
+/* second half of fitMiniBatch, lda.go:299-317 */
+static void blend_mini_batch(oracle_lda *l, mini_batch *mb) {
+    int64_t K = l->K;
     /* lda.go:299-300 -- outside any lock in the reference (racy when Processes>1) */
     double rhoPhi = schedule_calc(l->RhoPhi, l->rhoPhiT);
     l->rhoPhiT++;
@@ -338,7 +352,8 @@ static void *worker_main(void *p) {
             a->mb->end = a->mb->start + l->BatchSize;
         else
             a->mb->end = a->m->cols;
-        fit_mini_batch(l, a->mb, a->wc, a->nTheta, a->m);
+        estep_mini_batch(l, a->mb, a->wc, a->nTheta, a->m);
+        blend_mini_batch(l, a->mb);
     }
     return NULL;
 }
@@ -377,7 +392,8 @@ int oracle_lda_fit_transform(oracle_lda *l, const oracle_csc *m, const double *n
 
     int64_t numMiniBatches = (int64_t)ceil((double)c / (double)l->BatchSize);
     int64_t processes = l->Processes;
-    if (numMiniBatches < l->Processes) processes = numMiniBatches;
+    if (l->SyncGroup > 1) processes = l->SyncGroup;
+    if (numMiniBatches < processes) processes = numMiniBatches;
     if (processes < 1) processes = 1;
     mini_batch *miniBatches = (mini_batch *)calloc((size_t)processes, sizeof(mini_batch));
     for (int64_t i = 0; i < processes; i++) {
@@ -397,18 +413,42 @@ int oracle_lda_fit_transform(oracle_lda *l, const oracle_csc *m, const double *n
     pthread_mutex_t chan;
     pthread_mutex_init(&chan, NULL);
 
+    if (l->iterTimeCap < l->Iterations) {
+        l->iterTime = (double *)realloc(l->iterTime, sizeof(double) * (size_t)(l->Iterations + 1));
+        l->iterTimeCap = l->Iterations;
+    }
+    struct timespec ts0, ts1;
+    clock_gettime(CLOCK_MONOTONIC, &ts0);
+
     for (int64_t it = 0; it < l->Iterations; it++) {
         l->rhoThetaT++;
         int64_t next = 0;
+        if (l->SyncGroup > 1) {
+            for (int64_t j0 = 0; j0 < numMiniBatches; j0 += processes) {
+                int64_t n = numMiniBatches - j0 < processes ? numMiniBatches - j0 : processes;
+                for (int64_t g = 0; g < n; g++) {
+                    mini_batch *mb = &miniBatches[g];
+                    int64_t j = j0 + g;
+                    mini_batch_reset(mb, K, l->w);
+                    mb->start = j * l->BatchSize;
+                    mb->end = j < numMiniBatches - 1 ? mb->start + l->BatchSize : c;
+                    estep_mini_batch(l, mb, wc, nTheta, m);
+                }
+                for (int64_t g = 0; g < n; g++) blend_mini_batch(l, &miniBatches[g]);
+            }
+        } else
         for (int64_t p = 0; p < processes; p++) {
             args[p] = (worker_arg){l, &miniBatches[p], m, wc, nTheta, numMiniBatches, &next, &chan};
             if (processes > 1) pthread_create(&threads[p], NULL, worker_main, &args[p]);
         }
-        if (processes > 1)
+        if (l->SyncGroup > 1) {
+        } else if (processes > 1)
             for (int64_t p = 0; p < processes; p++) pthread_join(threads[p], NULL);
         else
             worker_main(&args[0]);
         l->iterationsRun = it + 1;
+        clock_gettime(CLOCK_MONOTONIC, &ts1);
+        l->iterTime[it] = (double)(ts1.tv_sec - ts0.tv_sec) + 1e-9 * (double)(ts1.tv_nsec - ts0.tv_nsec);
 
         if (l->PerplexityEvaluationFrequency > 0 && (it + 1) % l->PerplexityEvaluationFrequency == 0) {
             normalise_phi(l, l->nPhi, phiProb);
@@ -521,6 +561,7 @@ FIELD_RW(int64_t, ChangeEvaluationFrequency)
 FIELD_RW(double, Alpha)
 FIELD_RW(double, Eta)
 FIELD_RW(int64_t, Processes)
+FIELD_RW(int64_t, SyncGroup)
 FIELD_RW(double, rhoPhiT)
 FIELD_RW(double, rhoThetaT)
 FIELD_RW(double, wordsInCorpus)
@@ -539,6 +580,11 @@ int64_t oracle_lda_get_perpTrace(const oracle_lda *l, double *out, int64_t cap) 
     int64_t n = l->perpTraceLen < cap ? l->perpTraceLen : cap;
     if (out) memcpy(out, l->perpTrace, sizeof(double) * (size_t)n);
     return l->perpTraceLen;
+}
+int64_t oracle_lda_get_iterTime(const oracle_lda *l, double *out, int64_t cap) {
+    int64_t n = l->iterationsRun < cap ? l->iterationsRun : cap;
+    if (out && l->iterTime) memcpy(out, l->iterTime, sizeof(double) * (size_t)n);
+    return l->iterationsRun;
 }
 /* raw (un-normalised) state, for parity checks and for exporting a trained model */
 void oracle_lda_get_state(const oracle_lda *l, double *nphi, double *nz) {

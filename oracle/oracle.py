@@ -53,6 +53,8 @@ def lib():
             getattr(L, "oracle_lda_get_" + name).restype = C.c_int64
         L.oracle_lda_get_perpTrace.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         L.oracle_lda_get_perpTrace.restype = C.c_int64
+        L.oracle_lda_get_iterTime.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        L.oracle_lda_get_iterTime.restype = C.c_int64
         L.oracle_lda_get_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.oracle_lda_set_state.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]
         L.oracle_pcg_seed.argtypes = [C.c_void_p, C.c_uint64]
@@ -69,7 +71,7 @@ _FIELDS = {
     "Iterations": C.c_int64, "PerplexityTolerance": C.c_double, "PerplexityEvaluationFrequency": C.c_int64,
     "BatchSize": C.c_int64, "K": C.c_int64, "BurnInPasses": C.c_int64, "TransformationPasses": C.c_int64,
     "MeanChangeTolerance": C.c_double, "ChangeEvaluationFrequency": C.c_int64, "Alpha": C.c_double,
-    "Eta": C.c_double, "Processes": C.c_int64, "rhoPhiT": C.c_double, "rhoThetaT": C.c_double,
+    "Eta": C.c_double, "Processes": C.c_int64, "SyncGroup": C.c_int64, "rhoPhiT": C.c_double, "rhoThetaT": C.c_double,
     "wordsInCorpus": C.c_double,
 }
 
@@ -177,6 +179,14 @@ class LatentDirichletAllocation:
         n = lib().oracle_lda_get_perpTrace(self._h, None, 0)
         out = np.empty(n, dtype=np.float64)
         lib().oracle_lda_get_perpTrace(self._h, out.ctypes.data, n)
+        return out
+
+    @property
+    def iteration_times(self):
+        """seconds since the start of the iteration loop at the end of each iteration of the last fit"""
+        n = lib().oracle_lda_get_iterTime(self._h, None, 0)
+        out = np.empty(n, dtype=np.float64)
+        lib().oracle_lda_get_iterTime(self._h, out.ctypes.data, n)
         return out
 
     def FitTransform(self, m, nphi0=None, ntheta0=None):

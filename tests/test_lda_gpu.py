@@ -1,0 +1,341 @@
+"""CUDA parity tests (run on the B200 box with -m gpu).  Every test calls the product through the C ABI of
+liblda_b200.so (via nlp_b200.lda) and checks it against the CPU oracle (oracle/) on the same seeded inputs, against
+the reference's own fixtures (lda_test.go), or through size-independent properties.
+
+Stated tolerances (fp32 device state vs the reference's float64):
+  doc-topic matrix theta       max |delta| <= 2e-3 absolute   (values in [0,1])
+  per-iteration perplexity     relative    <= 1e-3            (north_star's bound; observed ~1e-5)
+  token indices / CSR handling bit-exact
+"""
+import numpy as np
+import pytest
+
+import corpus_synth
+import nlp_b200
+from nlp_b200 import _lib, rand
+from nlp_b200.lda import CSC, as_csc
+from oracle import oracle as O
+from tests.fixtures import EXPECTED_DOCS, FIT_CASES, FIXTURE_A, FIXTURE_B
+
+pytestmark = pytest.mark.gpu
+
+THETA_ATOL = 2e-3
+PERP_RTOL = 1e-3
+
+
+def new_lda(k, seed=0, **fields):
+    lda = nlp_b200.NewLatentDirichletAllocation(k)
+    lda.Rnd = rand.New(rand.NewSource(seed))
+    for f, v in fields.items():
+        assert hasattr(lda, f), f
+        setattr(lda, f, v)
+    return lda
+
+
+def new_oracle(k, seed=0, **fields):
+    o = O.LatentDirichletAllocation(k, seed=seed)
+    for f, v in fields.items():
+        setattr(o, f, v)
+    return o
+
+
+# ---- the reference's own tests, run against the CUDA path (lda_test.go) ------------------------------------
+@pytest.mark.parametrize("data,expected", FIT_CASES)
+def test_lda_fit(data, expected):
+    lda = new_lda(3)
+    lda.Fit(data)
+    components = lda.Components()
+    assert components.shape == (3, 9)
+    assert np.abs(components - expected).max() <= 0.01      # lda_test.go:80
+    assert np.abs(1 - components.sum(axis=1)).max() <= 1e-8  # lda_test.go:84
+
+
+@pytest.mark.parametrize("data", [FIXTURE_A, FIXTURE_B])
+def test_lda_fit_transform(data):
+    lda = new_lda(3)
+    theta = lda.FitTransform(data)
+    assert theta.shape == (3, 9)
+    assert np.abs(theta.T - EXPECTED_DOCS).max() <= 0.01  # lda_test.go:168
+    assert np.abs(1 - theta.sum(axis=0)).max() <= 1e-8    # lda_test.go:172
+
+
+@pytest.mark.parametrize("data", [FIXTURE_A, FIXTURE_B])
+def test_lda_transform(data):
+    lda = new_lda(3, PerplexityEvaluationFrequency=2)
+    theta = lda.FitTransform(data)
+    t_theta = lda.Transform(data)
+    assert np.abs(theta - t_theta).max() <= 0.035  # lda_test.go:231
+
+
+# ---- parity with the oracle -------------------------------------------------------------------------------
+@pytest.mark.parametrize("data", [FIXTURE_A, FIXTURE_B])
+def test_fixture_parity_trace(data):
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=60)
+    o = new_oracle(3, **f)
+    want = o.FitTransform(data)
+    lda = new_lda(3, **f)
+    got = lda.FitTransform(data)
+    assert lda.IterationsRun == o.iterationsRun == 60
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    np.testing.assert_allclose(lda.Components(), o.Components(), atol=THETA_ATOL)
+    nphi_o, nz_o = o.get_state()
+    nphi, nz = lda.GetState()
+    np.testing.assert_allclose(nz, nz_o, rtol=1e-3)
+    np.testing.assert_allclose(nphi, nphi_o, rtol=1e-2, atol=1e-3)
+    assert (lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus) == (o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus)
+
+
+def test_default_early_stop_matches_oracle():
+    # defaults: evaluation every 30 iterations, stop when |delta| < 1e-2 -> iteration 180
+    o = new_oracle(3)
+    o.Fit(FIXTURE_A)
+    lda = new_lda(3)
+    lda.Fit(FIXTURE_A)
+    assert lda.IterationsRun == o.iterationsRun == 180
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+
+
+def synth(D, W, mean_distinct, block=100, seed=12345):
+    indptr, ind, data = corpus_synth.generate(D, W, seed=seed, block=block, mean_distinct=mean_distinct, n_topics=16)
+    return CSC(W, D, indptr, ind, data)
+
+
+def run_pair(m, k, iters, seed=0, theta_atol=THETA_ATOL, **fields):
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=iters)
+    f.update(fields)
+    o = new_oracle(k, seed=seed, **f)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(k, seed=seed, **f)
+    got = lda.FitTransform(m)
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert np.abs(got - want).max() <= theta_atol
+    assert np.abs(1 - got.sum(axis=0)).max() <= 1e-8
+    return lda, o
+
+
+def test_config1_parity():
+    """BASELINE configs[0]: K=10, 1k docs x 5k vocab (~100k tokens), Processes=1, fixed seed, BatchSize=100"""
+    m = synth(1000, 5000, 100)
+    lda, o = run_pair(m, 10, 20)
+    rel = np.abs(np.array(lda.PerplexityTrace) / o.perplexity_trace - 1).max()
+    print("config1: max rel perplexity delta %.3g, final perplexity %.4f" % (rel, lda.PerplexityTrace[-1]))
+    assert lda.PerplexityTrace[-1] < lda.PerplexityTrace[0]
+    nphi_o, nz_o = o.get_state()
+    nphi, nz = lda.GetState()
+    np.testing.assert_allclose(nz, nz_o, rtol=1e-3)
+
+
+@pytest.mark.parametrize("k,D,W,b", [(1, 64, 200, 16), (3, 130, 300, 50), (16, 200, 500, 64), (33, 150, 400, 100),
+                                     (64, 150, 400, 40), (100, 300, 800, 100), (200, 120, 600, 32),
+                                     (256, 300, 1000, 128), (500, 60, 500, 32), (1024, 48, 400, 16)])
+def test_topic_widths(k, D, W, b):
+    """every (LANES, NV) kernel instantiation, pad lanes, ragged last minibatch"""
+    m = synth(D, W, 40, block=b)
+    run_pair(m, k, 4, BatchSize=b)
+
+
+def test_burn_in_passes_and_real_values():
+    m = synth(120, 300, 30)
+    rng = np.random.default_rng(1)
+    m = m._replace(data=m.data * rng.uniform(0.25, 2.5, size=m.data.size))  # TF-IDF-like non-integer values
+    run_pair(m, 8, 5, BurnInPasses=3, BatchSize=50)
+    run_pair(m, 8, 3, BurnInPasses=0, BatchSize=120)
+
+
+def test_burn_in_change_check_in_training():
+    # BurnInPasses >= ChangeEvaluationFrequency makes burnInDoc's early exit fire during training (lda.go:224-259)
+    m = synth(60, 200, 20)
+    run_pair(m, 5, 3, BurnInPasses=12, ChangeEvaluationFrequency=4, MeanChangeTolerance=1e-3, BatchSize=30)
+
+
+def test_unsorted_token_order_is_preserved():
+    # a CSC whose rows are NOT ascending inside a column: the sequential token chain must follow stored order
+    m = synth(80, 200, 25)
+    rng = np.random.default_rng(2)
+    ind, data = m.ind.copy(), m.data.copy()
+    for j in range(m.cols):
+        s, e = m.indptr[j], m.indptr[j + 1]
+        p = rng.permutation(e - s)
+        ind[s:e], data[s:e] = ind[s:e][p], data[s:e][p]
+    shuffled = m._replace(ind=ind, data=data)
+    run_pair(shuffled, 6, 5)
+    a = new_lda(6, Iterations=5).FitTransform(m)
+    b = new_lda(6, Iterations=5).FitTransform(shuffled)
+    assert np.abs(a - b).max() > 1e-6  # order matters (lda.go:236 -> 247), so the two inputs must differ
+
+
+def test_empty_documents_and_edge_shapes():
+    dense = np.zeros((12, 7))
+    dense[[0, 3, 5], 0] = [1, 2, 3]
+    dense[2, 2] = 4       # single-token document
+    dense[:, 4] = 1       # document using every word
+    # columns 1, 3, 5, 6 are empty documents
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=6, BatchSize=3)
+    o = new_oracle(4, **f)
+    want = o.FitTransform(dense)
+    lda = new_lda(4, **f)
+    got = lda.FitTransform(dense)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    t_o, p_o = o.Transform(dense, return_passes=True)
+    t, p = lda.Transform(dense, return_passes=True)
+    assert np.abs(t - t_o).max() <= THETA_ATOL
+    assert p.tolist() == p_o.tolist()
+    # a single document / single word
+    one = np.array([[3.0]])
+    assert np.abs(new_lda(2, Iterations=3).FitTransform(one) - new_oracle(2, Iterations=3).FitTransform(one)).max() <= 1e-5
+
+
+def test_sparse_inputs_match_dense():
+    import scipy.sparse as sp
+    a = new_lda(3, Iterations=10).FitTransform(FIXTURE_B)
+    for conv in (sp.csr_matrix, sp.csc_matrix, sp.coo_matrix, sp.dok_matrix):
+        b = new_lda(3, Iterations=10).FitTransform(conv(FIXTURE_B))
+        assert np.array_equal(a, b), conv.__name__
+
+
+def test_transform_and_perplexity_parity():
+    m = synth(300, 800, 40)
+    held = synth(90, 800, 40, seed=777)
+    f = dict(Iterations=15, PerplexityEvaluationFrequency=5, PerplexityTolerance=0.0)
+    lda, o = run_pair(m, 12, 15, **f)
+    # same model on both sides so that Transform parity is isolated from fit drift
+    nphi, nz = o.get_state()
+    lda.SetState(nphi, nz)
+    t_o, p_o = o.Transform(tuple(held), return_passes=True)
+    t, p = lda.Transform(held, return_passes=True)
+    assert np.abs(t - t_o).max() <= THETA_ATOL
+    assert np.mean(p == p_o) >= 0.95          # early exit happens at multiples of 30 (lda.go:224-259)
+    assert set(np.unique(p)) <= set(range(30, 501, 30)) | {500}
+    perp_o = o.Perplexity(tuple(held))
+    perp = lda.Perplexity(held)
+    assert abs(perp / perp_o - 1) <= PERP_RTOL
+    # the RNG streams advanced identically: D*K draws per Transform / Perplexity call (lda.go:422-426)
+    assert lda.Rnd.src.state == o.rnd_state
+
+
+def test_transform_pass_counts_fixture():
+    lda = new_lda(3, PerplexityEvaluationFrequency=2)
+    lda.FitTransform(FIXTURE_B)
+    assert lda.IterationsRun == 58
+    _, passes = lda.Transform(FIXTURE_B, return_passes=True)
+    assert passes.tolist() == [90, 90, 90, 90, 60, 450, 60, 60, 60]
+
+
+def test_refit_quirks():
+    # wordsInCorpus accumulates, rhoThetaT keeps counting, nPhi is re-drawn
+    f = dict(Iterations=4, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0)
+    lda, o = new_lda(3, **f), new_oracle(3, **f)
+    for _ in range(2):
+        got, want = lda.FitTransform(FIXTURE_A), o.FitTransform(FIXTURE_A)
+        assert np.abs(got - want).max() <= THETA_ATOL
+        np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert lda.wordsInCorpus == o.wordsInCorpus == 2 * FIXTURE_A.sum()
+    assert lda.rhoThetaT == o.rhoThetaT == 9
+    assert lda.Rnd.src.state == o.rnd_state
+
+
+# ---- bit-exact pieces -------------------------------------------------------------------------------------------
+def test_ingest_roundtrip_bit_exact():
+    import ctypes as C
+    m = synth(257, 1000, 30)
+    lda = new_lda(4)
+    h = lda._handle()
+    nnz = m.ind.size
+    indptr = np.zeros(m.cols + 1, dtype=np.int64)
+    ind = np.zeros(nnz, dtype=np.int32)
+    val = np.zeros(nnz, dtype=np.float32)
+    wc = np.zeros(m.cols, dtype=np.float64)
+    n = C.c_double(0)
+    _lib.check(_lib.lib().lda_b200_ingest_roundtrip(h, m.rows, m.cols, m.indptr.ctypes.data, m.ind.ctypes.data,
+                                                   m.data.ctypes.data, indptr.ctypes.data, ind.ctypes.data,
+                                                   val.ctypes.data, wc.ctypes.data, C.byref(n)), h)
+    assert np.array_equal(indptr, m.indptr)
+    assert np.array_equal(ind.astype(np.int64), m.ind)
+    assert np.array_equal(val.astype(np.float64), m.data)  # integer counts are exact in fp32
+    assert np.array_equal(wc, np.add.reduceat(m.data, m.indptr[:-1]))  # lda.go:476-480
+    assert n.value == m.data.sum()                                     # lda.go:481
+
+
+def test_device_pcg_init_is_bit_exact():
+    # Iterations = 0: the state read back is the initial draw of lda.go:199-205, produced on the GPU
+    W, D, K = 37, 11, 7
+    dense = np.ones((W, D))
+    lda = new_lda(K, seed=42, Iterations=0)
+    theta = lda.FitTransform(dense)
+    nphi, nz = lda.GetState()
+    ref = O.PCG(42)
+    nphi_ref = ref.fill(W * K, W * K).reshape(W, K)
+    ntheta_ref = ref.fill(D * K, D * K).reshape(D, K)
+    assert np.array_equal(nphi, nphi_ref.astype(np.float32).astype(np.float64))
+    np.testing.assert_allclose(nz, nphi_ref.astype(np.float32).astype(np.float64).sum(0), rtol=1e-12)
+    th32 = ntheta_ref.astype(np.float32).astype(np.float64)
+    np.testing.assert_allclose(theta, (th32 / th32.sum(1, keepdims=True)).T, rtol=1e-12)
+    assert lda.Rnd.src.state == ref.state
+    # host-drawn init (DeviceInit = False) gives the identical model
+    lda2 = new_lda(K, seed=42, Iterations=0, DeviceInit=False)
+    theta2 = lda2.FitTransform(dense)
+    assert np.array_equal(theta, theta2) and lda2.Rnd.src.state == ref.state
+
+
+def test_exported_init_replay():
+    # "same seeded init of nPhi/nTheta exported from the reference": arrays in, no RNG involved
+    m = synth(100, 300, 30)
+    K = 9
+    src = O.PCG(5)
+    nphi0 = src.fill(m.rows * K, m.rows * K)
+    ntheta0 = src.fill(m.cols * K, m.cols * K)
+    f = dict(Iterations=6, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0)
+    o = new_oracle(K, seed=99, **f)
+    want = o.FitTransform(tuple(m), nphi0=nphi0, ntheta0=ntheta0)
+    lda = new_lda(K, seed=1234, **f)
+    got = lda.FitTransform(m, nphi0=nphi0, ntheta0=ntheta0)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert lda.Rnd.src.state == rand.NewSource(1234).state  # untouched
+
+
+# ---- error behaviour -----------------------------------------------------------------------------------------------
+def test_errors():
+    lda = new_lda(3, Iterations=2)
+    with pytest.raises(_lib.LdaB200Error, match="before Fit"):
+        lda.Transform(FIXTURE_A)
+    bad = as_csc(FIXTURE_A)
+    bad.ind[4] = 9  # row index out of range
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.Fit(bad)
+    with pytest.raises(_lib.LdaB200Error, match="1024"):
+        new_lda(2048).Fit(FIXTURE_A)
+    with pytest.raises(_lib.LdaB200Error, match="BatchSize"):
+        new_lda(3, BatchSize=0).Fit(FIXTURE_A)
+    lda.Fit(FIXTURE_A)  # the handle is still usable after errors
+
+
+# ---- size-independent properties at a BASELINE-sized configuration -----------------------------------------------------
+def test_config2_properties():
+    """configs[1] shape (18,846 docs x 50k vocab, K=100): columns sum to 1, perplexity ends up falling, refit reproducible
+    up to the order of the fp32 reductions into nPhiHat."""
+    D, W, K, md = corpus_synth.shape("C2")
+    indptr, ind, data = corpus_synth.generate(D, W, block=4096, mean_distinct=md)
+    m = CSC(W, D, indptr, ind, data)
+    f = dict(Iterations=12, BatchSize=1024, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0)
+    lda = new_lda(K, **f)
+    theta = lda.FitTransform(m)
+    assert theta.shape == (K, D) and np.isfinite(theta).all() and theta.min() >= 0
+    assert np.abs(1 - theta.sum(axis=0)).max() <= 1e-8
+    tr = np.array(lda.PerplexityTrace)
+    print("config2 perplexity trace:", np.round(tr, 2).tolist())
+    # SCVB0 from a random init may rise for the first few iterations; it must be falling by the end
+    assert np.isfinite(tr).all() and np.all(np.diff(tr)[-3:] < 0) and tr[-1] < tr.max(), tr
+    comp = lda.Components()
+    assert np.abs(1 - comp.sum(axis=1)).max() <= 1e-8
+    lda2 = new_lda(K, **f)
+    theta2 = lda2.FitTransform(m)
+    np.testing.assert_allclose(lda2.PerplexityTrace, tr, rtol=1e-4)
+    assert np.abs(theta - theta2).max() <= 5e-3
+    # Transform of the training documents lands near FitTransform's theta (lda_test.go:179-235 at scale)
+    sub = CSC(W, 512, indptr[:513], ind[:indptr[512]], data[:indptr[512]])
+    t = lda.Transform(sub)
+    assert np.abs(t.sum(axis=0) - 1).max() <= 1e-8
+    assert np.mean(t.argmax(0) == theta[:, :512].argmax(0)) > 0.8
