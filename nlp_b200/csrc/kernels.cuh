@@ -326,21 +326,13 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *src, int64_t R
     const int RPB = blockDim.x / VPR;
     const int col = threadIdx.x % VPR;
     const int rslot = threadIdx.x / VPR;
-    double sx = 0, sy = 0, sz = 0, sw = 0;
-    for (int64_t r0 = (int64_t)blockIdx.x * RPB + rslot; r0 < R; r0 += (int64_t)gridDim.x * RPB * 64) {
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);  // short fp32 runs, flushed into float64
-        int64_t r = r0;
-        for (int i = 0; i < 64 && r < R; ++i, r += (int64_t)gridDim.x * RPB) {
-            const float4 t = ldg4(src + r * Kp + 4 * col);
-            acc.x += t.x;
-            acc.y += t.y;
-            acc.z += t.z;
-            acc.w += t.w;
-        }
-        sx += acc.x;
-        sy += acc.y;
-        sz += acc.z;
-        sw += acc.w;
+    double sx = 0, sy = 0, sz = 0, sw = 0;  // float64 throughout: Components' rows must sum to 1 within 1e-8 (lda_test.go:84)
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < R; r += (int64_t)gridDim.x * RPB) {
+        const float4 t = ldg4(src + r * Kp + 4 * col);
+        sx += (double)t.x;
+        sy += (double)t.y;
+        sz += (double)t.z;
+        sw += (double)t.w;
     }
     double *smd = reinterpret_cast<double *>(sm4);
     smd[4 * threadIdx.x + 0] = sx;

@@ -168,9 +168,10 @@ class LatentDirichletAllocation:
         self.FitTransform(m, _want_theta=False)
         return self
 
-    def FitTransform(self, m, _want_theta=True, nphi0=None, ntheta0=None):
+    def FitTransform(self, m, _want_theta=True, nphi0=None, ntheta0=None, out=None):
         """lda.go:463-542.  Returns the K x D doc-topic matrix (float64).  nphi0 / ntheta0 (not in the reference)
-        replace the RNG draws with an exported init, e.g. the reference's own, for deterministic parity runs."""
+        replace the RNG draws with an exported init, e.g. the reference's own, for deterministic parity runs; out
+        is an optional caller-owned K x D float64 result buffer (e.g. page-locked)."""
         csc = as_csc(m)
         h = self._handle()
         L = _lib.lib()
@@ -186,7 +187,11 @@ class LatentDirichletAllocation:
             raise ValueError("nlp: nphi0 must hold W*K values")
         if ntheta0 is not None and ntheta0.size != csc.cols * self.K:
             raise ValueError("nlp: ntheta0 must hold D*K values")
-        theta = np.zeros((self.K, csc.cols), dtype=np.float64) if _want_theta else None
+        theta = None
+        if _want_theta:
+            theta = np.zeros((self.K, csc.cols), dtype=np.float64) if out is None else out
+            if theta.shape != (self.K, csc.cols) or theta.dtype != np.float64 or not theta.flags.c_contiguous:
+                raise ValueError("nlp: out must be a C-contiguous float64 K x D array")
         cap = self.Iterations // self.PerplexityEvaluationFrequency + 1 if self.PerplexityEvaluationFrequency > 0 else 1
         trace = np.zeros(cap, dtype=np.float64)
         n_evals, iters = C.c_int32(0), C.c_int32(0)
