@@ -224,6 +224,209 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Throughput kernel for K > 64 (one document per warp, LANES = 32).  Same arithmetic as above, restated so
+// that the per-token dependent chain and the instruction count are minimal:
+//   * registers hold tha_k = nTheta[j,k] + alpha.  With c_k = (nPhi[i,k]+eta) invZ_k (one FMA from the row),
+//       S = sum_k c_k tha_k,  r = 1/S,  q = 1-(1-rho)^v:
+//       tha_k' = tha_k (1-q + q wc r c_k) + alpha q          == Eqn 9 applied to gamma_k = c_k tha_k r
+//       nPhiHat[i,k] += (N/b) r c_k tha_k                     (main pass)
+//     i.e. 4 FMAs per topic in a burn-in pass, 6 in the main pass.
+//   * the document's passes form one continuous token stream: word ids / q of the next 32-token tile and the
+//     nPhi rows of the next P tokens are always in flight, across tile and pass boundaries.
+//   * token groups are padded to P with (word 0, q = 0) entries, which leave tha unchanged exactly and are
+//     predicated out of the reduction, so the inner loop carries no bounds checks.
+//   * FULLK: K == 128*NV, so the row stride is a compile-time constant and no slice is masked.
+__device__ __forceinline__ float fast_rcp(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r * fmaf(-x, r, 2.0f);  // one Newton step: ~0.5 ulp
+}
+
+struct Tile {
+    int wi;   // word id of the token this lane holds (0 for padding)
+    float q;  // 1-(1-rho)^v of that token (0 for padding)
+};
+
+template <int NV, int P, bool FULLK, bool FIT>
+__global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
+    const int lane = threadIdx.x & 31;
+    const int Kp = FULLK ? 128 * NV : a.Kp;
+    const float alpha = a.alpha, eta = a.eta;
+    const float *__restrict__ nphi = a.nphi + 4 * lane;
+    const int32_t *__restrict__ ind = a.ind;
+    const float *__restrict__ val = a.val;
+    const float *__restrict__ tab = a.log1m_rho;
+    const int passes = a.passes;
+    const int total_passes = passes + (FIT ? 1 : 0);
+
+    bool ok[NV];
+    float4 iz[NV], ez[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        ok[v] = FULLK || 4 * (v * 32 + lane) < Kp;
+        iz[v] = ok[v] ? ldg4(a.inv_z + 4 * (v * 32 + lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        ez[v] = make_float4(eta * iz[v].x, eta * iz[v].y, eta * iz[v].z, eta * iz[v].w);
+    }
+    auto row_load = [&](int w, int v) -> float4 {
+        return ok[v] ? ldg4(nphi + (int64_t)w * Kp + 128 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+
+    for (;;) {
+        int d0 = 0;
+        if (lane == 0) d0 = atomicAdd(a.doc_counter, 1);
+        d0 = __shfl_sync(FULL, d0, 0);
+        if (a.doc_begin + d0 >= a.doc_end) break;
+        const int doc = order ? order[a.doc_begin + d0] : a.doc_begin + d0;
+        const int64_t base = a.doc_ptr[doc];
+        const int len = (int)(a.doc_ptr[doc + 1] - base);
+        if (len == 0 || total_passes == 0) {  // no tokens: nTheta row keeps its value
+            if (a.passes_out && lane == 0) a.passes_out[doc] = len > 0 ? 0 : -1;
+            continue;
+        }
+        const float wcj = a.wc[doc];
+        float *trow = a.theta + (int64_t)doc * Kp + 4 * lane;
+        float4 tha[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 t = ok[v] ? *reinterpret_cast<const float4 *>(trow + 128 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tha[v] = make_float4(t.x + alpha, t.y + alpha, t.z + alpha, t.w + alpha);
+        }
+        const int n_tiles = (len + 31) >> 5;
+        auto load_tile = [&](int pi, int ti) -> Tile {
+            const int my = (ti << 5) + lane;
+            Tile t;
+            if (my < len) {
+                t.wi = ind[base + my];
+                t.q = -expm1f(val[base + my] * tab[min(pi + 1, passes)]);  // lda.go:231 / :274
+            } else {
+                t.wi = 0;
+                t.q = 0.f;
+            }
+            return t;
+        };
+        auto theta_sum = [&]() -> double {  // sum_k nTheta[j,k]  (lda.go:226-229, 252-255)
+            double s = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v]) s += ((double)(tha[v].x - alpha) + (tha[v].y - alpha)) + ((double)(tha[v].z - alpha) + (tha[v].w - alpha));
+            return group_sum_d<32>(s);
+        };
+
+        int pi = 0, ti = 0, executed = 0;
+        double prev = 0.0;
+        Tile cur = load_tile(0, 0);
+        float4 buf[P][NV];
+#pragma unroll
+        for (int s = 0; s < P; ++s) {
+            const int w = __shfl_sync(FULL, cur.wi, s);
+#pragma unroll
+            for (int v = 0; v < NV; ++v) buf[s][v] = row_load(w, v);
+        }
+        for (;;) {
+            const bool last_tile = ti == n_tiles - 1;
+            const int npi = last_tile ? pi + 1 : pi, nti = last_tile ? 0 : ti + 1;
+            const bool has_next = npi < total_passes;
+            Tile nxt;
+            nxt.wi = 0;
+            nxt.q = 0.f;
+            if (has_next) nxt = load_tile(npi, nti);
+            const int counter = pi + 1;
+            const bool burn = pi < passes;
+            const bool chk = burn && a.change_freq > 0 && counter % a.change_freq == 0;
+            if (ti == 0 && chk && 1 < passes) prev = theta_sum();  // lda.go:224-230
+
+            const int tile0 = ti << 5;
+            const int npad = (min(32, len - tile0) + P - 1) / P * P;
+            const bool main_pass = FIT && !burn;
+            for (int t0 = 0; t0 < npad; t0 += P) {
+                const bool from_cur = t0 + P < npad;
+                const int wsrc = from_cur ? cur.wi : nxt.wi;
+                const int lsrc = from_cur ? t0 + P : 0;
+#pragma unroll
+                for (int s = 0; s < P; ++s) {
+                    const int t = t0 + s;
+                    const float qt = __shfl_sync(FULL, cur.q, t);
+                    float4 c[NV];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        c[v].x = fmaf(buf[s][v].x, iz[v].x, ez[v].x);
+                        c[v].y = fmaf(buf[s][v].y, iz[v].y, ez[v].y);
+                        c[v].z = fmaf(buf[s][v].z, iz[v].z, ez[v].z);
+                        c[v].w = fmaf(buf[s][v].w, iz[v].w, ez[v].w);
+                    }
+                    const int wn = __shfl_sync(FULL, wsrc, lsrc + s);
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) buf[s][v] = row_load(wn, v);
+
+                    float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        p0 = fmaf(c[v].x, tha[v].x, p0);
+                        p1 = fmaf(c[v].y, tha[v].y, p1);
+                        p0 = fmaf(c[v].z, tha[v].z, p0);
+                        p1 = fmaf(c[v].w, tha[v].w, p1);
+                    }
+                    const float r = fast_rcp(group_sum<32>(p0 + p1));
+                    const float keep = 1.0f - qt;
+                    const float mix = qt * wcj * r;
+                    const float aq = alpha * qt;
+                    if (FIT && main_pass) {
+                        if (tile0 + t < len) {
+                            const int w = __shfl_sync(FULL, cur.wi, t);
+                            const float sc = a.hat_scale * r;
+                            float *hp = a.nphi_hat + (int64_t)w * Kp + 4 * lane;
+#pragma unroll
+                            for (int v = 0; v < NV; ++v)
+                                if (ok[v])
+                                    red_add_v4(hp + 128 * v, make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y,
+                                                                         sc * c[v].z * tha[v].z, sc * c[v].w * tha[v].w));
+                        }
+                    }
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        tha[v].x = fmaf(tha[v].x, fmaf(mix, c[v].x, keep), aq);
+                        tha[v].y = fmaf(tha[v].y, fmaf(mix, c[v].y, keep), aq);
+                        tha[v].z = fmaf(tha[v].z, fmaf(mix, c[v].z, keep), aq);
+                        tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
+                    }
+                }
+            }
+            if (last_tile) {
+                if (burn) executed = counter;
+                if (chk && counter < passes) {  // lda.go:251-259
+                    const double sm = theta_sum();
+                    if (fabs(sm - prev) / (double)a.K < (double)a.change_tol) {
+                        if (!FIT) break;
+                        // burn-in converged early: continue with the sufficient-statistics pass (lda.go:274)
+                        pi = passes;
+                        ti = 0;
+                        cur = load_tile(pi, 0);
+#pragma unroll
+                        for (int s = 0; s < P; ++s) {
+                            const int w = __shfl_sync(FULL, cur.wi, s);
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) buf[s][v] = row_load(w, v);
+                        }
+                        continue;
+                    }
+                }
+            }
+            if (!has_next) break;
+            cur = nxt;
+            pi = npi;
+            ti = nti;
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+            if (ok[v])
+                *reinterpret_cast<float4 *>(trow + 128 * v) =
+                    make_float4(fmaxf(tha[v].x - alpha, 0.f), fmaxf(tha[v].y - alpha, 0.f), fmaxf(tha[v].z - alpha, 0.f),
+                                fmaxf(tha[v].w - alpha, 0.f));
+        if (a.passes_out && lane == 0) a.passes_out[doc] = executed;
+    }
+}
+
 // ln(1 - S/(Tau + t0 + c)^Kappa), c = 0..n-1  (LearningSchedule.Calc, lda.go:30-32), evaluated in float64
 __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, int n, float *out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

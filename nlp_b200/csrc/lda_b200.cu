@@ -39,6 +39,8 @@ struct Corpus {
     float *val = nullptr;
     float *wc = nullptr;
     float *theta = nullptr;
+    int *order = nullptr;  // documents of each launch range, longest first (order inside a minibatch is free:
+                           // documents only interact through commutative sums)
     double n_local = 0;  // sum of values of the local shard
     double n_global = 0;
 };
@@ -160,6 +162,7 @@ void free_corpus(Corpus &c) {
     dfree(&c.val);
     dfree(&c.wc);
     dfree(&c.theta);
+    dfree(&c.order);
     c = Corpus();
 }
 
@@ -181,28 +184,45 @@ int validate_config(lda_b200_handle *h, const lda_b200_config *c) {
 
 // ---- kernel dispatch on the topic width ------------------------------------------------------------
 template <bool FIT>
-int launch_docs(lda_b200_handle *h, const DocsArgs &a) {
+int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order) {
     const int vecs = a.Kp / 4;
     const int n_docs = a.doc_end - a.doc_begin;
     if (n_docs <= 0) return 0;
-    auto go = [&](auto kern, int lanes) -> int {
+    auto grid_of = [&](auto kern, int gpw, int *grid) -> int {
         int occ = 1;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0));
         if (occ < 1) occ = 1;
-        const int gpw = 32 / lanes;
         const int64_t warps = ((int64_t)n_docs + gpw - 1) / gpw;
-        const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * occ);
+        *grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * occ);
+        return 0;
+    };
+    // narrow topic axes: several documents per warp, natural order
+    auto narrow = [&](auto kern, int lanes) -> int {
+        int grid;
+        TRY(grid_of(kern, 32 / lanes, &grid));
         kern<<<grid, 256, 0, h->stream>>>(a);
         KCHECK();
         return 0;
     };
-    if (vecs <= 4) return go(scvb0_docs_kernel<4, 1, 4, FIT>, 4);
-    if (vecs <= 8) return go(scvb0_docs_kernel<8, 1, 4, FIT>, 8);
-    if (vecs <= 16) return go(scvb0_docs_kernel<16, 1, 4, FIT>, 16);
-    if (vecs <= 32) return go(scvb0_docs_kernel<32, 1, 4, FIT>, 32);
-    if (vecs <= 64) return go(scvb0_docs_kernel<32, 2, 4, FIT>, 32);
-    if (vecs <= 128) return go(scvb0_docs_kernel<32, 4, 2, FIT>, 32);
-    return go(scvb0_docs_kernel<32, 8, 2, FIT>, 32);
+    // K > 64: one document per warp, longest documents first
+    auto wide = [&](auto kern) -> int {
+        int grid;
+        TRY(grid_of(kern, 1, &grid));
+        kern<<<grid, 256, 0, h->stream>>>(a, order);
+        KCHECK();
+        return 0;
+    };
+    if (vecs <= 4) return narrow(scvb0_docs_kernel<4, 1, 4, FIT>, 4);
+    if (vecs <= 8) return narrow(scvb0_docs_kernel<8, 1, 4, FIT>, 8);
+    if (vecs <= 16) return narrow(scvb0_docs_kernel<16, 1, 4, FIT>, 16);
+    if (vecs < 32) return wide(scvb0_docs32_kernel<1, 4, false, FIT>);
+    if (vecs == 32) return wide(scvb0_docs32_kernel<1, 4, true, FIT>);
+    if (vecs < 64) return wide(scvb0_docs32_kernel<2, 4, false, FIT>);
+    if (vecs == 64) return wide(scvb0_docs32_kernel<2, 4, true, FIT>);
+    if (vecs < 128) return wide(scvb0_docs32_kernel<4, 2, false, FIT>);
+    if (vecs == 128) return wide(scvb0_docs32_kernel<4, 2, true, FIT>);
+    if (vecs < 256) return wide(scvb0_docs32_kernel<8, 1, false, FIT>);
+    return wide(scvb0_docs32_kernel<8, 1, true, FIT>);
 }
 
 int launch_perplexity(lda_b200_handle *h, const PerpArgs &a) {
@@ -353,7 +373,7 @@ int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const doub
 
 // Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
 int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                  const double *data, double *wc64_out /*device, optional*/) {
+                  const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order) {
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
     free_corpus(c);
@@ -384,6 +404,18 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     TRY(dalloc(h, &c.wc, (size_t)Dl));
     CU(cudaMemcpyAsync(c.doc_ptr, lp.data(), ((size_t)Dl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    {   // longest-first processing order inside every launch range (a minibatch for Fit, everything for Transform)
+        std::vector<int> ord((size_t)Dl);
+        for (int64_t i = 0; i < Dl; ++i) ord[(size_t)i] = (int)i;
+        const int64_t blk = per_minibatch_order ? c.b : std::max<int64_t>(Dl, 1);
+        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
+            const int64_t l1 = std::min(Dl, l0 + blk);
+            std::stable_sort(ord.begin() + l0, ord.begin() + l1,
+                             [&](int x, int y) { return lp[x + 1] - lp[x] > lp[y + 1] - lp[y]; });
+        }
+        TRY(dalloc(h, &c.order, (size_t)Dl));
+        CU(cudaMemcpy(c.order, ord.data(), (size_t)Dl * sizeof(int), cudaMemcpyHostToDevice));
+    }
 
     const int64_t chunk = (int64_t)(h->stage_bytes / 8);
     for (const Segment &s : c.segs) {
@@ -523,7 +555,7 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, int32_t *pa
     CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
     DocsArgs a = docs_args(h, c, T);
     a.passes_out = dpass;
-    int rc = launch_docs<false>(h, a);
+    int rc = launch_docs<false>(h, a, c.order);
     if (!rc && passes_out_host) {
         std::vector<int32_t> tmp((size_t)c.Dl);
         cudaError_t e = cudaMemcpyAsync(tmp.data(), dpass, (size_t)c.Dl * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
@@ -703,7 +735,7 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     TRY(refresh_nz_from_nphi(h));
     TRY(refresh_inv_z(h));
 
-    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr));
+    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true));
     TRY(init_theta(h, h->fitc, ntheta0, rnd, draws));
     if (!ntheta0) draws += (uint64_t)D * (uint64_t)h->K;
     if (rnd && draws) advance(rnd, draws);
@@ -769,7 +801,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 a.hat_scale = (float)(ctr->words_in_corpus / (double)b_actual * (R > 1 ? cg : 1.0));
                 int slot;
                 TRY(ev_begin(h, 0, &slot));
-                TRY(launch_docs<true>(h, a));
+                TRY(launch_docs<true>(h, a, c.order));
                 TRY(ev_end(h, slot));
             }
             if (R > 1)
@@ -863,7 +895,7 @@ int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, con
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr);
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false);
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
     if (!rc) rc = run_transform(h, c, rho_theta_t, passes_out);
@@ -884,7 +916,7 @@ int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, co
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr);  // wordCount = c.n_global, lda.go:372-385
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false);  // wordCount = c.n_global, lda.go:372-385
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
     if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr);
@@ -990,7 +1022,7 @@ int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const in
     Corpus c;
     double *wc64 = nullptr;
     int rc = dalloc(h, &wc64, (size_t)std::max<int64_t>(D, 1));
-    if (!rc) rc = upload_corpus(h, c, W, D, indptr, ind, data, wc64);
+    if (!rc) rc = upload_corpus(h, c, W, D, indptr, ind, data, wc64, true);
     auto back = [&]() -> int {
         if (indptr_out) CU(cudaMemcpyAsync(indptr_out, c.doc_ptr, (size_t)(c.Dl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
         if (ind_out) CU(cudaMemcpyAsync(ind_out, c.ind, (size_t)c.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
