@@ -22,8 +22,9 @@
  *  - one handle = one model on one GPU, used by one caller at a time.  With a
  *    communicator of R ranks (lda_b200_comm_init) each rank owns the global minibatches
  *    m with m % R == rank (lda.go:504-528 hands consecutive minibatches to workers);
- *    every rank is given the same global indptr, and reads only the ranges of ind/data
- *    (and writes only the columns of theta_out) that belong to its own minibatches.
+ *    every rank passes global-shaped arguments (indptr[D+1], theta_out K x D) but the library
+ *    reads only the indptr entries and ind/data ranges (and writes only the theta_out columns)
+ *    of its own minibatches, so a rank may leave other ranks' documents empty in its view.
  */
 #ifndef LDA_B200_H
 #define LDA_B200_H
@@ -98,6 +99,18 @@ const char *lda_b200_last_error(const lda_b200_handle *h);
  * lda_b200_comm_unique_id on rank 0 and distributed by the host. */
 int lda_b200_comm_unique_id(void *id128);
 int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const void *id128);
+
+/* Host-only planning arithmetic of the multi-GPU step (no GPU needed; exported so it can be tested on CPU).
+ * lda.go:299-317 applied for the n_s minibatches of one step in index order, all computed from the same nPhi:
+ *   nPhi' = A nPhi + sum_g c_g nPhiHat_g,   rho_g = RhoPhi.Calc(rho_phi_t + g),
+ *   A = prod_g (1 - rho_g),   c_g = rho_g prod_{h>g} (1 - rho_h).
+ * Rank g scales its nPhiHat by c_g, one allreduce(sum) follows, every rank applies nPhi' = A nPhi + sum. */
+int lda_b200_plan_step(const lda_b200_schedule *rho_phi, double rho_phi_t, int32_t n_s, int32_t rank, double *A,
+                       double *c_rank);
+/* global document ranges [begin,end) owned by `rank` (minibatch m -> rank m % nranks), in local row order;
+ * returns the number of ranges (at most cap are written) */
+int64_t lda_b200_plan_shard(int64_t D, int64_t batch_size, int32_t rank, int32_t nranks, int64_t *seg_begin,
+                            int64_t *seg_end, int64_t cap);
 
 /* FitTransform, lda.go:463-542 (Fit, lda.go:211, is the same call with theta_out == NULL).
  *  nphi0   W*K  values [w*K+k] replacing the draws of lda.go:199-205, or NULL

@@ -39,6 +39,9 @@ SYMBOLS = {
     "lda_b200_last_error": (C.c_char_p, [_P]),
     "lda_b200_comm_unique_id": (C.c_int, [_P]),
     "lda_b200_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, _P]),
+    "lda_b200_plan_step": (C.c_int, [C.POINTER(Schedule), C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_double),
+                                     C.POINTER(C.c_double)]),
+    "lda_b200_plan_shard": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int64]),
     "lda_b200_fit": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters), _P, _P,
                                C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lda_b200_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, _P, _P]),

@@ -783,15 +783,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             // Eqn 7/8 for n_s minibatches blended one after the other (lda.go:299-317), each computed from the
             // same nPhi snapshot: nPhi' = A nPhi + sum_g c_g nPhiHat_g
             double A = 1.0, cg = 0.0;
-            {
-                double tail = 1.0;
-                for (int g = n_s - 1; g >= 0; --g) {
-                    const double rho = rho_calc(cfg.rho_phi, ctr->rho_phi_t + g);
-                    if (g == h->rank) cg = rho * tail;
-                    tail *= (1.0 - rho);
-                }
-                A = tail;
-            }
+            lda_b200_plan_step(&cfg.rho_phi, ctr->rho_phi_t, n_s, h->rank, &A, &cg);
             if (h->rank < n_s) {
                 const int64_t m = s * R + h->rank;
                 const int64_t b_actual = (m < M - 1) ? b : c.D - m * b;  // lda.go:513-518, :268
@@ -989,6 +981,32 @@ int lda_b200_set_state(lda_b200_handle *h, int64_t W, const double *nphi, const 
     CU(cudaStreamSynchronize(h->stream));
     h->fitted = true;
     return 0;
+}
+
+// ---- host-only planning helpers -----------------------------------------------------------------------------
+int lda_b200_plan_step(const lda_b200_schedule *rho_phi, double rho_phi_t, int32_t n_s, int32_t rank, double *A,
+                       double *c_rank) {
+    if (!rho_phi || n_s < 0) return LDA_B200_EINVAL;
+    double tail = 1.0, cg = 0.0;
+    for (int g = n_s - 1; g >= 0; --g) {
+        const double rho = rho_calc(*rho_phi, rho_phi_t + g);
+        if (g == rank) cg = rho * tail;
+        tail *= (1.0 - rho);
+    }
+    if (A) *A = tail;
+    if (c_rank) *c_rank = cg;
+    return 0;
+}
+
+int64_t lda_b200_plan_shard(int64_t D, int64_t batch_size, int32_t rank, int32_t nranks, int64_t *seg_begin,
+                            int64_t *seg_end, int64_t cap) {
+    if (D < 0 || batch_size < 1 || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+    const std::vector<Segment> s = make_segments(D, batch_size, rank, nranks);
+    for (size_t i = 0; i < s.size() && (int64_t)i < cap; ++i) {
+        if (seg_begin) seg_begin[i] = s[i].g0;
+        if (seg_end) seg_end[i] = s[i].g1;
+    }
+    return (int64_t)s.size();
 }
 
 // ---- PCG host helpers ------------------------------------------------------------------------------------
