@@ -42,6 +42,8 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--workload", default="C3", choices=["C1", "C2", "C3", "C4"])
     p.add_argument("--batch-size", type=int, default=8192)
+    p.add_argument("--processes-per-gpu", type=int, default=4,
+                   help="minibatches in flight per GPU (the reference's Processes / number of GPUs)")
     p.add_argument("--docs", type=int, default=0, help="override the number of documents (debug)")
     p.add_argument("--cpu-docs-per-worker", type=int, default=256)
     p.add_argument("--skip-cpu", action="store_true")
@@ -247,7 +249,7 @@ def ours(args):
         lda.Rnd = rand.New(rand.NewSource(0))
         lda.BatchSize = b
         lda.Iterations = iterations
-        lda.Processes = world
+        lda.Processes = world * args.processes_per_gpu
         return lda
 
     B = 1  # BurnInPasses default
@@ -299,13 +301,14 @@ def ours(args):
         "kernel_share_of_step": mb_ms.value / dev_ms if dev_ms else None,
         "blend_kernel": {"launches": bl_n.value, "avg_launch_ms": (bl_ms.value / bl_n.value) if bl_n.value else None,
                          "achieved_GBps": (16.0 * K * W * bl_n.value / (bl_ms.value * 1e-3) / 1e9) if bl_ms.value else None},
-        "whole_step_achieved_GBps": (alg_bytes(nnz, D, K, B) + ((D + b - 1) // b) * 16.0 * K * W) * steps / (ms * 1e-3) / 1e9 / world,
+        "whole_step_achieved_GBps": (alg_bytes(nnz, D, K, B) + bl_n.value / steps * 16.0 * K * W * world) * steps / (ms * 1e-3) / 1e9 / world,
     }
 
     # ---- e2e: the public call on host buffers ---------------------------------------------------------------------------
     e2e = None
     if not args.skip_e2e:
-        out = torch.empty((K, D), dtype=torch.float64).pin_memory().numpy() if world == 1 else np.zeros((K, D))
+        out_t = torch.empty((K, D), dtype=torch.float64, pin_memory=True)   # page-locked result buffer
+        out = out_t.numpy()
         lda2 = new_lda(steps)
         lda2._handle()
         barrier()
@@ -349,9 +352,12 @@ def ours(args):
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: LDA SCVB0 fit, K=%d, %d docs x %d vocab, %d nnz (Zipfian planted-LDA corpus, seed 12345)"
-                       % (cfgname, K, D, W, nnz), "batch_size": b, "burn_in_passes": B,
-                       "parallelism": "dp%d (minibatch m -> GPU m %% %d, NCCL allreduce of nPhiHat per step)" % (world, world),
-                       "step": "one SCVB0 iteration over all %d minibatches" % ((D + b - 1) // b),
+                       % (cfgname, K, D, W, nnz), "batch_size": b, "processes": world * args.processes_per_gpu,
+                       "burn_in_passes": B,
+                       "parallelism": "dp%d (minibatch m -> GPU m %% %d, %d minibatches per GPU per step, NCCL allreduce of "
+                                      "nPhiHat per step)" % (world, world, args.processes_per_gpu),
+                       "step": "one SCVB0 iteration over all %d minibatches (%d launches per GPU)" % (
+                           (D + b - 1) // b, -(-((D + b - 1) // b) // (world * args.processes_per_gpu))),
                        "l2": "inputs larger than L2 (CSC + nTheta = %.1f GB per GPU per step)" % (
                            (nnz_local * 8 + docs_local * K * 4) / 1e9),
                        "token_visits_per_step": visits_per_step, "corpus_generation_s": round(t_gen, 1)},

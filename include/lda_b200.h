@@ -58,8 +58,10 @@ typedef struct {
     int32_t transformation_passes;          /* lda.go:93  TransformationPasses */
     int32_t perplexity_evaluation_frequency;/* lda.go:79  */
     int32_t change_evaluation_frequency;    /* lda.go:103 */
-    int32_t processes;                      /* lda.go:134 Processes: informational; the degree of
-                                               parallelism is the communicator size */
+    int32_t processes;                      /* lda.go:134 Processes: minibatches in flight per step.  With R ranks
+                                               each GPU processes max(1, processes / R) (at most 16) consecutive
+                                               minibatches of its own in one launch, all from the same nPhi
+                                               snapshot, blended afterwards in index order (lda.go:299-317) */
     double perplexity_tolerance;            /* lda.go:75  */
     double mean_change_tolerance;           /* lda.go:98  */
     double alpha, eta;                      /* lda.go:106,109 */

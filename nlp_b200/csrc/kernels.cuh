@@ -57,8 +57,13 @@ struct DocsArgs {
     int change_freq;         // ChangeEvaluationFrequency
     float change_tol;        // MeanChangeTolerance
     float alpha, eta;
-    float hat_scale;         // wordsInCorpus / batchSize (x allreduce coefficient), lda.go:293
+    // sufficient-statistics scale of each minibatch covered by this launch: wordsInCorpus / batchSize (lda.go:293)
+    // times the coefficient of that minibatch in the combined blend (lda_b200_plan_step); a launch covers up to
+    // MAX_CONCURRENT_MB consecutive local minibatches of mb_docs documents (the reference's `Processes`).
+    float hat_scale[16];
+    int mb_docs;
 };
+constexpr int MAX_CONCURRENT_MB = 16;
 
 // One pass over the tokens of the documents currently held by this warp's groups.
 //   Eqn 5 (lda.go:234-242 / 277-284): gamma_k ∝ (nPhi[i,k]+eta)(nTheta[j,k]+alpha)/(nZ[k]+eta*W), normalised
@@ -68,7 +73,7 @@ struct DocsArgs {
 // which keeps full relative accuracy when rho is small (the reference calls math.Pow 2K times per token).
 template <int LANES, int NV, int P, bool MAIN>
 __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int len, int maxlen, float l1m, float wcj,
-                                           int g, float4 (&th)[NV], const float4 (&iz)[NV], const bool (&ok)[NV]) {
+                                           float hat_scale, int g, float4 (&th)[NV], const float4 (&iz)[NV], const bool (&ok)[NV]) {
     for (int tile = 0; tile < maxlen; tile += LANES) {
         const int my = tile + g;
         const bool has = my < len;
@@ -129,7 +134,7 @@ __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int 
                             th[v].w = fmaf(keep, th[v].w, mix * gm[v].w);
                         }
                         if (MAIN) {
-                            const float sc = a.hat_scale * r;
+                            const float sc = hat_scale * r;
 #pragma unroll
                             for (int v = 0; v < NV; ++v)
                                 if (ok[v])
@@ -201,7 +206,7 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
                 prev = group_sum_d<LANES>(s);
             }
             const float l1m = a.log1m_rho[counter];  // lda.go:231
-            token_pass<LANES, NV, P, false>(a, base, done ? 0 : len, maxlen, l1m, wcj, g, th, iz, ok);
+            token_pass<LANES, NV, P, false>(a, base, done ? 0 : len, maxlen, l1m, wcj, 0.f, g, th, iz, ok);
             if (!done) executed = counter;
             if (chk && counter < a.passes) {  // lda.go:251-259
                 double s = 0.0;
@@ -213,7 +218,8 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
         }
         if (FIT) {
             const float l1m = a.log1m_rho[a.passes];  // lda.go:274
-            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, g, th, iz, ok);
+            const float hs = valid ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
+            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, hs, g, th, iz, ok);
         }
         if (valid) {
 #pragma unroll
@@ -231,16 +237,26 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
 //       S = sum_k c_k tha_k,  r = 1/S,  q = 1-(1-rho)^v:
 //       tha_k' = tha_k (1-q + q wc r c_k) + alpha q          == Eqn 9 applied to gamma_k = c_k tha_k r
 //       nPhiHat[i,k] += (N/b) r c_k tha_k                     (main pass)
-//     i.e. 4 FMAs per topic in a burn-in pass, 6 in the main pass.
-//   * the document's passes form one continuous token stream: word ids / q of the next 32-token tile and the
-//     nPhi rows of the next P tokens are always in flight, across tile and pass boundaries.
-//   * token groups are padded to P with (word 0, q = 0) entries, which leave tha unchanged exactly and are
-//     predicated out of the reduction, so the inner loop carries no bounds checks.
+//   * the nPhi rows are staged through a per-warp shared-memory ring of R rows filled with cp.async
+//     (LDGSTS, L2-only): the row of the token R positions ahead in the document's token stream -- which runs
+//     on across tile and pass boundaries -- is always in flight.  Each lane copies, and later reads, only its
+//     own 16-byte slices of a row, so the ring needs no barrier: the per-thread cp.async group order is enough.
+//   * word ids and q = 1-(1-rho)^v of the current 32-token tile live in registers (one token per lane, so
+//     expm1f costs 1/32 per token); the next tile is loaded one tile ahead.
 //   * FULLK: K == 128*NV, so the row stride is a compile-time constant and no slice is masked.
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r * fmaf(-x, r, 2.0f);  // one Newton step: ~0.5 ulp
+}
+__device__ __forceinline__ void cp_async16(float4 *smem_dst, const float *gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 struct Tile {
@@ -248,9 +264,17 @@ struct Tile {
     float q;  // 1-(1-rho)^v of that token (0 for padding)
 };
 
-template <int NV, int P, bool FULLK, bool FIT>
-__global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
+constexpr int docs32_ring_rows(int NV) { return NV == 1 ? 8 : NV == 2 ? 6 : NV == 4 ? 4 : 3; }
+constexpr int docs32_min_blocks(int NV) { return NV <= 2 ? 4 : NV == 4 ? 2 : 1; }
+constexpr int docs32_smem_bytes(int NV) { return 8 * docs32_ring_rows(NV) * NV * 512; }
+
+template <int NV, bool FULLK, bool FIT>
+__global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
+    constexpr int R = docs32_ring_rows(NV);
+    constexpr bool EZ = NV <= 2;  // keep eta*invZ in registers only where the register budget allows
+    extern __shared__ float4 ring_all[];
     const int lane = threadIdx.x & 31;
+    float4 *ring = ring_all + (threadIdx.x >> 5) * (R * NV * 32) + lane;  // slot s, slice v: ring[(s*NV+v)*32]
     const int Kp = FULLK ? 128 * NV : a.Kp;
     const float alpha = a.alpha, eta = a.eta;
     const float *__restrict__ nphi = a.nphi + 4 * lane;
@@ -261,15 +285,21 @@ __global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, con
     const int total_passes = passes + (FIT ? 1 : 0);
 
     bool ok[NV];
-    float4 iz[NV], ez[NV];
+    float4 iz[NV], ez[EZ ? NV : 1];
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
         ok[v] = FULLK || 4 * (v * 32 + lane) < Kp;
         iz[v] = ok[v] ? ldg4(a.inv_z + 4 * (v * 32 + lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        ez[v] = make_float4(eta * iz[v].x, eta * iz[v].y, eta * iz[v].z, eta * iz[v].w);
+        if (EZ) ez[v] = make_float4(eta * iz[v].x, eta * iz[v].y, eta * iz[v].z, eta * iz[v].w);
     }
-    auto row_load = [&](int w, int v) -> float4 {
-        return ok[v] ? ldg4(nphi + (int64_t)w * Kp + 128 * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+    // asynchronous copy of this lane's slices of row w into ring slot `slot`; always closes one cp.async group
+    auto issue = [&](int slot, int w) {
+        if (w >= 0) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v]) cp_async16(ring + (slot * NV + v) * 32, nphi + (int64_t)w * Kp + 128 * v);
+        }
+        cp_async_commit();
     };
 
     for (;;) {
@@ -285,6 +315,7 @@ __global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, con
             continue;
         }
         const float wcj = a.wc[doc];
+        const float hat_scale = FIT ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
         float *trow = a.theta + (int64_t)doc * Kp + 4 * lane;
         float4 tha[NV];
 #pragma unroll
@@ -313,16 +344,30 @@ __global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, con
             return group_sum_d<32>(s);
         };
 
+        // look-ahead cursor: position of the next row to request = (pass la_pass, token la_idx); la_w is its word id
+        int la_idx, la_pass, la_w, slot;
+        auto la_advance = [&]() {
+            if (++la_idx == len) {
+                la_idx = 0;
+                ++la_pass;
+            }
+            la_w = la_pass < total_passes ? ind[base + la_idx] : -1;
+        };
+        auto prime = [&](int first_pass) {
+            la_idx = 0;
+            la_pass = first_pass;
+            la_w = ind[base];
+            for (int s = 0; s < R; ++s) {
+                issue(s, la_w);
+                la_advance();
+            }
+            slot = 0;
+        };
+
         int pi = 0, ti = 0, executed = 0;
         double prev = 0.0;
         Tile cur = load_tile(0, 0);
-        float4 buf[P][NV];
-#pragma unroll
-        for (int s = 0; s < P; ++s) {
-            const int w = __shfl_sync(FULL, cur.wi, s);
-#pragma unroll
-            for (int v = 0; v < NV; ++v) buf[s][v] = row_load(w, v);
-        }
+        prime(0);
         for (;;) {
             const bool last_tile = ti == n_tiles - 1;
             const int npi = last_tile ? pi + 1 : pi, nti = last_tile ? 0 : ti + 1;
@@ -336,60 +381,59 @@ __global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, con
             const bool chk = burn && a.change_freq > 0 && counter % a.change_freq == 0;
             if (ti == 0 && chk && 1 < passes) prev = theta_sum();  // lda.go:224-230
 
-            const int tile0 = ti << 5;
-            const int npad = (min(32, len - tile0) + P - 1) / P * P;
+            const int ntile = min(32, len - (ti << 5));
             const bool main_pass = FIT && !burn;
-            for (int t0 = 0; t0 < npad; t0 += P) {
-                const bool from_cur = t0 + P < npad;
-                const int wsrc = from_cur ? cur.wi : nxt.wi;
-                const int lsrc = from_cur ? t0 + P : 0;
+            for (int t = 0; t < ntile; ++t) {
+                const float qt = __shfl_sync(FULL, cur.q, t);
+                cp_async_wait<R - 1>();  // the oldest outstanding group (this token's row) has landed
+                float4 c[NV];
 #pragma unroll
-                for (int s = 0; s < P; ++s) {
-                    const int t = t0 + s;
-                    const float qt = __shfl_sync(FULL, cur.q, t);
-                    float4 c[NV];
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        c[v].x = fmaf(buf[s][v].x, iz[v].x, ez[v].x);
-                        c[v].y = fmaf(buf[s][v].y, iz[v].y, ez[v].y);
-                        c[v].z = fmaf(buf[s][v].z, iz[v].z, ez[v].z);
-                        c[v].w = fmaf(buf[s][v].w, iz[v].w, ez[v].w);
+                for (int v = 0; v < NV; ++v) {
+                    const float4 row = ok[v] ? ring[(slot * NV + v) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (EZ) {
+                        c[v].x = fmaf(row.x, iz[v].x, ez[v].x);
+                        c[v].y = fmaf(row.y, iz[v].y, ez[v].y);
+                        c[v].z = fmaf(row.z, iz[v].z, ez[v].z);
+                        c[v].w = fmaf(row.w, iz[v].w, ez[v].w);
+                    } else {
+                        c[v].x = (row.x + eta) * iz[v].x;
+                        c[v].y = (row.y + eta) * iz[v].y;
+                        c[v].z = (row.z + eta) * iz[v].z;
+                        c[v].w = (row.w + eta) * iz[v].w;
                     }
-                    const int wn = __shfl_sync(FULL, wsrc, lsrc + s);
-#pragma unroll
-                    for (int v = 0; v < NV; ++v) buf[s][v] = row_load(wn, v);
+                }
+                issue(slot, la_w);  // refill the slot just consumed with the row R positions ahead
+                la_advance();
+                slot = slot + 1 == R ? 0 : slot + 1;
 
-                    float p0 = 0.f, p1 = 0.f;
+                float p0 = 0.f, p1 = 0.f;
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        p0 = fmaf(c[v].x, tha[v].x, p0);
-                        p1 = fmaf(c[v].y, tha[v].y, p1);
-                        p0 = fmaf(c[v].z, tha[v].z, p0);
-                        p1 = fmaf(c[v].w, tha[v].w, p1);
-                    }
-                    const float r = fast_rcp(group_sum<32>(p0 + p1));
-                    const float keep = 1.0f - qt;
-                    const float mix = qt * wcj * r;
-                    const float aq = alpha * qt;
-                    if (FIT && main_pass) {
-                        if (tile0 + t < len) {
-                            const int w = __shfl_sync(FULL, cur.wi, t);
-                            const float sc = a.hat_scale * r;
-                            float *hp = a.nphi_hat + (int64_t)w * Kp + 4 * lane;
+                for (int v = 0; v < NV; ++v) {
+                    p0 = fmaf(c[v].x, tha[v].x, p0);
+                    p1 = fmaf(c[v].y, tha[v].y, p1);
+                    p0 = fmaf(c[v].z, tha[v].z, p0);
+                    p1 = fmaf(c[v].w, tha[v].w, p1);
+                }
+                const float r = fast_rcp(group_sum<32>(p0 + p1));
+                const float keep = 1.0f - qt;
+                const float mix = qt * wcj * r;
+                const float aq = alpha * qt;
+                if (FIT && main_pass) {
+                    const int w = __shfl_sync(FULL, cur.wi, t);
+                    const float sc = hat_scale * r;
+                    float *hp = a.nphi_hat + (int64_t)w * Kp + 4 * lane;
 #pragma unroll
-                            for (int v = 0; v < NV; ++v)
-                                if (ok[v])
-                                    red_add_v4(hp + 128 * v, make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y,
-                                                                         sc * c[v].z * tha[v].z, sc * c[v].w * tha[v].w));
-                        }
-                    }
+                    for (int v = 0; v < NV; ++v)
+                        if (ok[v])
+                            red_add_v4(hp + 128 * v, make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y,
+                                                                 sc * c[v].z * tha[v].z, sc * c[v].w * tha[v].w));
+                }
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        tha[v].x = fmaf(tha[v].x, fmaf(mix, c[v].x, keep), aq);
-                        tha[v].y = fmaf(tha[v].y, fmaf(mix, c[v].y, keep), aq);
-                        tha[v].z = fmaf(tha[v].z, fmaf(mix, c[v].z, keep), aq);
-                        tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
-                    }
+                for (int v = 0; v < NV; ++v) {
+                    tha[v].x = fmaf(tha[v].x, fmaf(mix, c[v].x, keep), aq);
+                    tha[v].y = fmaf(tha[v].y, fmaf(mix, c[v].y, keep), aq);
+                    tha[v].z = fmaf(tha[v].z, fmaf(mix, c[v].z, keep), aq);
+                    tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
                 }
             }
             if (last_tile) {
@@ -397,17 +441,13 @@ __global__ void __launch_bounds__(256) scvb0_docs32_kernel(const DocsArgs a, con
                 if (chk && counter < passes) {  // lda.go:251-259
                     const double sm = theta_sum();
                     if (fabs(sm - prev) / (double)a.K < (double)a.change_tol) {
+                        cp_async_wait<0>();  // rows requested for the passes that will not run
                         if (!FIT) break;
                         // burn-in converged early: continue with the sufficient-statistics pass (lda.go:274)
                         pi = passes;
                         ti = 0;
                         cur = load_tile(pi, 0);
-#pragma unroll
-                        for (int s = 0; s < P; ++s) {
-                            const int w = __shfl_sync(FULL, cur.wi, s);
-#pragma unroll
-                            for (int v = 0; v < NV; ++v) buf[s][v] = row_load(w, v);
-                        }
+                        prime(pi);
                         continue;
                     }
                 }

@@ -33,6 +33,7 @@ struct Corpus {
     int64_t Dl = 0;      // local documents
     int64_t nnz = 0;     // local non-zeros
     int64_t b = 0;       // block (minibatch) size used for sharding
+    int conc = 1;        // minibatches per launch on this GPU (Processes / ranks), fit only
     std::vector<Segment> segs;
     int64_t *doc_ptr = nullptr;
     int32_t *ind = nullptr;
@@ -204,25 +205,29 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order) {
         KCHECK();
         return 0;
     };
-    // K > 64: one document per warp, longest documents first
-    auto wide = [&](auto kern) -> int {
-        int grid;
-        TRY(grid_of(kern, 1, &grid));
-        kern<<<grid, 256, 0, h->stream>>>(a, order);
+    // K > 64: one document per warp, longest documents first, nPhi rows staged through a shared-memory ring
+    auto wide = [&](auto kern, int nv) -> int {
+        const int smem = docs32_smem_bytes(nv);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        if (occ < 1) occ = 1;
+        const int grid = (int)std::min<int64_t>(((int64_t)n_docs + 7) / 8, (int64_t)h->sms * occ);
+        kern<<<grid, 256, smem, h->stream>>>(a, order);
         KCHECK();
         return 0;
     };
     if (vecs <= 4) return narrow(scvb0_docs_kernel<4, 1, 4, FIT>, 4);
     if (vecs <= 8) return narrow(scvb0_docs_kernel<8, 1, 4, FIT>, 8);
     if (vecs <= 16) return narrow(scvb0_docs_kernel<16, 1, 4, FIT>, 16);
-    if (vecs < 32) return wide(scvb0_docs32_kernel<1, 4, false, FIT>);
-    if (vecs == 32) return wide(scvb0_docs32_kernel<1, 4, true, FIT>);
-    if (vecs < 64) return wide(scvb0_docs32_kernel<2, 4, false, FIT>);
-    if (vecs == 64) return wide(scvb0_docs32_kernel<2, 4, true, FIT>);
-    if (vecs < 128) return wide(scvb0_docs32_kernel<4, 2, false, FIT>);
-    if (vecs == 128) return wide(scvb0_docs32_kernel<4, 2, true, FIT>);
-    if (vecs < 256) return wide(scvb0_docs32_kernel<8, 1, false, FIT>);
-    return wide(scvb0_docs32_kernel<8, 1, true, FIT>);
+    if (vecs < 32) return wide(scvb0_docs32_kernel<1, false, FIT>, 1);
+    if (vecs == 32) return wide(scvb0_docs32_kernel<1, true, FIT>, 1);
+    if (vecs < 64) return wide(scvb0_docs32_kernel<2, false, FIT>, 2);
+    if (vecs == 64) return wide(scvb0_docs32_kernel<2, true, FIT>, 2);
+    if (vecs < 128) return wide(scvb0_docs32_kernel<4, false, FIT>, 4);
+    if (vecs == 128) return wide(scvb0_docs32_kernel<4, true, FIT>, 4);
+    if (vecs < 256) return wide(scvb0_docs32_kernel<8, false, FIT>, 8);
+    return wide(scvb0_docs32_kernel<8, true, FIT>, 8);
 }
 
 int launch_perplexity(lda_b200_handle *h, const PerpArgs &a) {
@@ -379,6 +384,8 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     free_corpus(c);
     c.D = D;
     c.b = h->cfg.batch_size;
+    // the reference runs `Processes` minibatches concurrently (lda.go:487-528); here R GPUs x conc per GPU
+    c.conc = per_minibatch_order ? std::min(MAX_CONCURRENT_MB, std::max(1, h->cfg.processes / h->nranks)) : 1;
     c.segs = make_segments(D, c.b, h->rank, h->nranks);
     int64_t Dl = 0;
     for (const Segment &s : c.segs) Dl += s.g1 - s.g0;
@@ -407,7 +414,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     {   // longest-first processing order inside every launch range (a minibatch for Fit, everything for Transform)
         std::vector<int> ord((size_t)Dl);
         for (int64_t i = 0; i < Dl; ++i) ord[(size_t)i] = (int)i;
-        const int64_t blk = per_minibatch_order ? c.b : std::max<int64_t>(Dl, 1);
+        const int64_t blk = per_minibatch_order ? c.b * c.conc : std::max<int64_t>(Dl, 1);
         for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
             const int64_t l1 = std::min(Dl, l0 + blk);
             std::stable_sort(ord.begin() + l0, ord.begin() + l1,
@@ -540,7 +547,8 @@ DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
     a.change_tol = (float)h->cfg.mean_change_tolerance;
     a.alpha = (float)h->cfg.alpha;
     a.eta = (float)h->cfg.eta;
-    a.hat_scale = 0.f;
+    for (float &x : a.hat_scale) x = 0.f;
+    a.mb_docs = (int)std::max<int64_t>(1, c.b);
     return a;
 }
 
@@ -764,7 +772,8 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
     const int R = h->nranks;
     const int64_t b = c.b;
     const int64_t M = (c.D + b - 1) / b;      // numMiniBatches, lda.go:487
-    const int64_t nsteps = (M + R - 1) / R;
+    const int G = R * c.conc;                 // minibatches in flight per step (the reference's `processes`, lda.go:488-491)
+    const int64_t nsteps = (M + G - 1) / G;
     const int B = cfg.burn_in_passes;
     int evals = 0, ran = 0;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
@@ -779,18 +788,28 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
         ctr->rho_theta_t += 1;  // lda.go:502
         TRY(fill_rho_table(h, ctr->rho_theta_t, B + 1));
         for (int64_t s = 0; s < nsteps; ++s) {
-            const int n_s = (int)std::min<int64_t>(R, M - s * R);  // minibatches processed in this step
-            // Eqn 7/8 for n_s minibatches blended one after the other (lda.go:299-317), each computed from the
-            // same nPhi snapshot: nPhi' = A nPhi + sum_g c_g nPhiHat_g
-            double A = 1.0, cg = 0.0;
-            lda_b200_plan_step(&cfg.rho_phi, ctr->rho_phi_t, n_s, h->rank, &A, &cg);
-            if (h->rank < n_s) {
-                const int64_t m = s * R + h->rank;
+            // minibatches s*G .. s*G+n_s-1 are all computed from the same nPhi snapshot and then blended one after
+            // the other in index order (lda.go:299-317 n_s times):  nPhi' = A nPhi + sum_g c_g nPhiHat_g
+            const int n_s = (int)std::min<int64_t>(G, M - s * G);
+            DocsArgs a = docs_args(h, c, B);
+            int64_t l_first = -1, l_last = -1;
+            double A = 1.0, c_single = 0.0;
+            for (int g = 0; g < n_s; ++g) {
+                const int64_t m = s * G + g;
+                double cg = 0.0;
+                lda_b200_plan_step(&cfg.rho_phi, ctr->rho_phi_t, n_s, g, &A, &cg);
+                if (g == 0) c_single = cg;  // used only when n_s == 1; identical on every rank
+                if (m % R != h->rank) continue;
+                const int64_t l = m / R;  // local minibatch index on this rank
+                if (l_first < 0) l_first = l;
+                l_last = l;
                 const int64_t b_actual = (m < M - 1) ? b : c.D - m * b;  // lda.go:513-518, :268
-                DocsArgs a = docs_args(h, c, B);
-                a.doc_begin = (int)(s * b);
-                a.doc_end = (int)(s * b + b_actual);
-                a.hat_scale = (float)(ctr->words_in_corpus / (double)b_actual * (R > 1 ? cg : 1.0));
+                // a lone minibatch keeps rho out of the accumulated values (blend applies it); otherwise fold c_g in
+                a.hat_scale[l - l_first] = (float)(ctr->words_in_corpus / (double)b_actual * (n_s > 1 ? cg : 1.0));
+            }
+            if (l_first >= 0) {
+                a.doc_begin = (int)(l_first * b);
+                a.doc_end = (int)std::min<int64_t>(c.Dl, (l_last + 1) * b);
                 int slot;
                 TRY(ev_begin(h, 0, &slot));
                 TRY(launch_docs<true>(h, a, c.order));
@@ -810,7 +829,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             ba.K = h->K;
             ba.Kp = h->Kp;
             ba.Ad = A;
-            ba.Cd = (R > 1) ? 1.0 : cg;
+            ba.Cd = (n_s > 1) ? 1.0 : c_single;
             ba.A = (float)ba.Ad;
             ba.C = (float)ba.Cd;
             ba.etaW = cfg.eta * (double)h->W;

@@ -135,6 +135,22 @@ def test_topic_widths(k, D, W, b):
     run_pair(m, k, 4, BatchSize=b)
 
 
+@pytest.mark.parametrize("k,procs,b,D", [(12, 3, 40, 410), (256, 4, 64, 300), (100, 16, 16, 200), (8, 40, 10, 95)])
+def test_processes_concurrent_minibatches(k, procs, b, D):
+    """Processes = P on one GPU: P minibatches per launch from one nPhi snapshot, blended in index order -- the
+    oracle's SyncGroup = P restatement of lda.go:487-528 (at most 16 per launch)."""
+    m = synth(D, 500, 30, block=b)
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=4, BatchSize=b)
+    o = new_oracle(k, SyncGroup=min(procs, 16), **f)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(k, Processes=procs, **f)
+    got = lda.FitTransform(m)
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    assert (lda.rhoPhiT, lda.rhoThetaT) == (o.rhoPhiT, o.rhoThetaT)
+    np.testing.assert_allclose(lda.GetState()[1], o.get_state()[1], rtol=1e-3)
+
+
 def test_burn_in_passes_and_real_values():
     m = synth(120, 300, 30)
     rng = np.random.default_rng(1)
@@ -205,8 +221,10 @@ def test_transform_and_perplexity_parity():
     lda.SetState(nphi, nz)
     t_o, p_o = o.Transform(tuple(held), return_passes=True)
     t, p = lda.Transform(held, return_passes=True)
-    assert np.abs(t - t_o).max() <= THETA_ATOL
-    assert np.mean(p == p_o) >= 0.95          # early exit happens at multiples of 30 (lda.go:224-259)
+    same = p == p_o
+    assert same.mean() >= 0.95                # early exit happens at multiples of 30 (lda.go:224-259); a borderline
+    assert np.abs(t - t_o)[:, same].max() <= THETA_ATOL   # fp32/float64 decision moves a document by 30 passes,
+    assert np.abs(t - t_o).max() <= 0.035                 # which lda_test.go:231 tolerates with 0.035
     assert set(np.unique(p)) <= set(range(30, 501, 30)) | {500}
     perp_o = o.Perplexity(tuple(held))
     perp = lda.Perplexity(held)
