@@ -5,7 +5,9 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <string>
@@ -141,29 +143,52 @@ int fail(lda_b200_handle *h, int code, const char *fmt, ...) {
         CU(cudaPeekAtLastError());    \
     } while (0)
 
+// LDA_B200_TIMING=1: wall-clock phases of the host-facing calls on stderr (diagnostic)
+struct PhaseTimer {
+    bool on;
+    cudaStream_t st;
+    double t0;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec + 1e-9 * ts.tv_nsec;
+    }
+    explicit PhaseTimer(cudaStream_t s) : on(getenv("LDA_B200_TIMING") != nullptr), st(s), t0(on ? now() : 0) {}
+    void lap(const char *what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "[lda_b200] %-28s %8.2f ms\n", what, 1e3 * (t - t0));
+        t0 = t;
+    }
+};
+
+// Device buffers come from the device's stream-ordered memory pool (cudaMallocAsync) with the release threshold
+// lifted, so the multi-GB corpus / result buffers of one call are recycled by the next instead of paying
+// cudaMalloc / cudaFree (tens to hundreds of ms at these sizes) on every Fit / Transform.
 template <typename T>
 int dalloc(lda_b200_handle *h, T **p, size_t n) {
     if (*p) {
-        cudaFree(*p);
+        cudaFreeAsync(*p, h->stream);
         *p = nullptr;
     }
     if (n == 0) n = 1;
-    CU(cudaMalloc((void **)p, n * sizeof(T)));
+    CU(cudaMallocAsync((void **)p, n * sizeof(T), h->stream));
     return 0;
 }
 template <typename T>
-void dfree(T **p) {
-    if (*p) cudaFree(*p);
+void dfree(lda_b200_handle *h, T **p) {
+    if (*p) cudaFreeAsync(*p, h->stream);
     *p = nullptr;
 }
 
-void free_corpus(Corpus &c) {
-    dfree(&c.doc_ptr);
-    dfree(&c.ind);
-    dfree(&c.val);
-    dfree(&c.wc);
-    dfree(&c.theta);
-    dfree(&c.order);
+void free_corpus(lda_b200_handle *h, Corpus &c) {
+    dfree(h, &c.doc_ptr);
+    dfree(h, &c.ind);
+    dfree(h, &c.val);
+    dfree(h, &c.wc);
+    dfree(h, &c.theta);
+    dfree(h, &c.order);
     c = Corpus();
 }
 
@@ -381,7 +406,8 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
                   const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order) {
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
-    free_corpus(c);
+    PhaseTimer pt(h->stream);
+    free_corpus(h, c);
     c.D = D;
     c.b = h->cfg.batch_size;
     // the reference runs `Processes` minibatches concurrently (lda.go:487-528); here R GPUs x conc per GPU
@@ -404,6 +430,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         }
     }
     c.nnz = lp[Dl];
+    pt.lap("ingest: local indptr");
     if (c.nnz > 0 && (!ind || !data)) return fail(h, LDA_B200_EINVAL, "ind/data is NULL");
     TRY(dalloc(h, &c.doc_ptr, (size_t)Dl + 1));
     TRY(dalloc(h, &c.ind, (size_t)c.nnz));
@@ -411,18 +438,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     TRY(dalloc(h, &c.wc, (size_t)Dl));
     CU(cudaMemcpyAsync(c.doc_ptr, lp.data(), ((size_t)Dl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
-    {   // longest-first processing order inside every launch range (a minibatch for Fit, everything for Transform)
-        std::vector<int> ord((size_t)Dl);
-        for (int64_t i = 0; i < Dl; ++i) ord[(size_t)i] = (int)i;
-        const int64_t blk = per_minibatch_order ? c.b * c.conc : std::max<int64_t>(Dl, 1);
-        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
-            const int64_t l1 = std::min(Dl, l0 + blk);
-            std::stable_sort(ord.begin() + l0, ord.begin() + l1,
-                             [&](int x, int y) { return lp[x + 1] - lp[x] > lp[y + 1] - lp[y]; });
-        }
-        TRY(dalloc(h, &c.order, (size_t)Dl));
-        CU(cudaMemcpy(c.order, ord.data(), (size_t)Dl * sizeof(int), cudaMemcpyHostToDevice));
-    }
+    pt.lap("ingest: cudaMalloc corpus");
 
     const int64_t chunk = (int64_t)(h->stage_bytes / 8);
     for (const Segment &s : c.segs) {
@@ -439,6 +455,26 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
             KCHECK();
         }
     }
+    {   // Longest-first processing order inside every launch range (`conc` minibatches for Fit, everything for
+        // Transform), by a stable counting sort on the document length; runs on the host while the copies above are
+        // in flight.
+        std::vector<int> ord((size_t)Dl);
+        std::vector<int> cnt;
+        const int64_t blk = per_minibatch_order ? c.b * c.conc : std::max<int64_t>(Dl, 1);
+        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
+            const int64_t l1 = std::min(Dl, l0 + blk);
+            int64_t maxlen = 0;
+            for (int64_t l = l0; l < l1; ++l) maxlen = std::max(maxlen, lp[l + 1] - lp[l]);
+            cnt.assign((size_t)maxlen + 2, 0);
+            for (int64_t l = l0; l < l1; ++l) cnt[(size_t)(maxlen - (lp[l + 1] - lp[l])) + 1]++;   // key: descending length
+            for (size_t k = 1; k < cnt.size(); ++k) cnt[k] += cnt[k - 1];
+            for (int64_t l = l0; l < l1; ++l) ord[(size_t)(l0 + cnt[(size_t)(maxlen - (lp[l + 1] - lp[l]))]++)] = (int)l;
+        }
+        TRY(dalloc(h, &c.order, (size_t)Dl));
+        CU(cudaMemcpyAsync(c.order, ord.data(), (size_t)Dl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));  // ord / lp are host temporaries
+    }
+    pt.lap("ingest: H2D + narrow + length sort");
     CU(cudaMemsetAsync(h->dacc + 1, 0, sizeof(double), h->stream));
     if (Dl > 0) {
         doc_wc_kernel<<<grid_for(Dl * 32, 256, h->sms * 8), 256, 0, h->stream>>>(c.doc_ptr, c.val, (int)Dl, c.wc, wc64_out, h->dacc + 1);
@@ -449,6 +485,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     CU(cudaMemcpyAsync(h->h_pinned + 1, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     c.n_global = h->h_pinned[0];
+    pt.lap("ingest: wc + N");
     int bad;
     memcpy(&bad, h->h_pinned + 1, sizeof(int));
     if (bad) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)W);
@@ -507,8 +544,10 @@ int eval_perplexity(lda_b200_handle *h, const Corpus &c, double sum, double *out
 // normaliseTheta + transposed float64 copy (lda.go:452, 541) into the caller's K x D matrix
 int write_theta_out(lda_b200_handle *h, const Corpus &c, double *theta_out) {
     if (!theta_out || c.Dl == 0) return 0;
+    PhaseTimer pt(h->stream);
     double *dout = nullptr;
     TRY(dalloc(h, &dout, (size_t)h->K * c.Dl));
+    pt.lap("theta_out: cudaMalloc");
     transpose_out_kernel<true><<<(unsigned)((c.Dl + 31) / 32), 256, 0, h->stream>>>(c.theta, c.Dl, h->K, h->Kp, nullptr, dout, c.Dl);
     h->launches++;
     cudaError_t e = cudaPeekAtLastError();
@@ -520,7 +559,9 @@ int write_theta_out(lda_b200_handle *h, const Corpus &c, double *theta_out) {
         }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dout);
+    pt.lap("theta_out: normalise + D2H");
+    cudaFreeAsync(dout, h->stream);
+    pt.lap("theta_out: free");
     if (e != cudaSuccess) return fail(h, LDA_B200_ECUDA, "theta read-back failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -572,7 +613,7 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, int32_t *pa
         for (const Segment &s : c.segs)
             for (int64_t g = s.g0; g < s.g1 && !rc; ++g) passes_out_host[g] = tmp[(size_t)(s.l0 + g - s.g0)];
     }
-    if (dpass) cudaFree(dpass);
+    if (dpass) cudaFreeAsync(dpass, h->stream);
     return rc;
 }
 
@@ -621,6 +662,10 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         CU(cudaGetDeviceProperties(&prop, device));
         h->sms = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;
+        CU(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         TRY(dalloc(h, &h->ticket, 1));
         TRY(dalloc(h, &h->doc_counter, 1));
         TRY(dalloc(h, &h->err_flag, 1));
@@ -647,19 +692,20 @@ void lda_b200_destroy(lda_b200_handle *h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->comm) nccl().CommDestroy(h->comm);
-    free_corpus(h->fitc);
-    dfree(&h->nphi);
-    dfree(&h->nphi_hat);
-    dfree(&h->nz);
-    dfree(&h->nzhat);
-    dfree(&h->colsum);
-    dfree(&h->inv_z);
-    dfree(&h->inv_colsum);
-    dfree(&h->ticket);
-    dfree(&h->doc_counter);
-    dfree(&h->err_flag);
-    dfree(&h->dacc);
-    dfree(&h->rho_tab);
+    free_corpus(h, h->fitc);
+    dfree(h, &h->nphi);
+    dfree(h, &h->nphi_hat);
+    dfree(h, &h->nz);
+    dfree(h, &h->nzhat);
+    dfree(h, &h->colsum);
+    dfree(h, &h->inv_z);
+    dfree(h, &h->inv_colsum);
+    dfree(h, &h->ticket);
+    dfree(h, &h->doc_counter);
+    dfree(h, &h->err_flag);
+    dfree(h, &h->dacc);
+    dfree(h, &h->rho_tab);
+    if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stage) cudaFree(h->stage);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     for (EventPair &p : h->ev_pool) {
@@ -725,6 +771,7 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
     if ((!nphi0 || !ntheta0) && !rnd) return fail(h, LDA_B200_EINVAL, "neither initial values nor a PCG state were given");
     CU(cudaSetDevice(h->device));
+    PhaseTimer pt(h->stream);
     h->fit_open = false;
     // init (lda.go:193-206): nPhi/nZ are re-allocated on every fit, no warm start
     h->W = 0;
@@ -742,9 +789,12 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     }
     TRY(refresh_nz_from_nphi(h));
     TRY(refresh_inv_z(h));
+    pt.lap("fit_begin: model alloc + nPhi init");
 
     TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true));
+    pt.t0 = PhaseTimer::now();
     TRY(init_theta(h, h->fitc, ntheta0, rnd, draws));
+    pt.lap("fit_begin: nTheta init");
     if (!ntheta0) draws += (uint64_t)D * (uint64_t)h->K;
     if (rnd && draws) advance(rnd, draws);
 
@@ -876,8 +926,11 @@ int lda_b200_fit_end(lda_b200_handle *h, double *theta_out) {
     if (!h) return LDA_B200_EINVAL;
     if (!h->fit_open) return fail(h, LDA_B200_ESTATE, "lda_b200_fit_end without lda_b200_fit_begin");
     CU(cudaSetDevice(h->device));
+    PhaseTimer pt(h->stream);
     int rc = write_theta_out(h, h->fitc, theta_out);
-    free_corpus(h->fitc);
+    pt.t0 = PhaseTimer::now();
+    free_corpus(h, h->fitc);
+    pt.lap("fit_end: free corpus");
     h->fit_open = false;
     return rc;
 }
@@ -887,10 +940,13 @@ int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr
                  lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
                  int32_t *iters_run) {
     if (!h) return LDA_B200_EINVAL;
+    PhaseTimer pt(h->stream);
     TRY(lda_b200_fit_begin(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr));
+    pt.lap("fit: begin total");
     int rc = lda_b200_fit_iterate(h, h->cfg.iterations, ctr, perp_trace, perp_cap, n_evals, iters_run, nullptr, nullptr);
+    pt.lap("fit: iterations");
     if (rc) {
-        free_corpus(h->fitc);
+        free_corpus(h, h->fitc);
         h->fit_open = false;
         return rc;
     }
@@ -915,7 +971,7 @@ int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, con
         cudaError_t e = cudaStreamSynchronize(h->stream);
         if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "transform failed: %s", cudaGetErrorString(e));
     }
-    free_corpus(c);
+    free_corpus(h, c);
     return rc;
 }
 
@@ -932,7 +988,7 @@ int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, co
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
     if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr);
     if (!rc) rc = eval_perplexity(h, c, c.n_global, out);
-    free_corpus(c);
+    free_corpus(h, c);
     return rc;
 }
 
@@ -952,7 +1008,7 @@ int lda_b200_components(lda_b200_handle *h, double *out) {
     cudaError_t e = cudaPeekAtLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, (size_t)h->K * h->W * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-    cudaFree(dout);
+    cudaFreeAsync(dout, h->stream);
     if (e != cudaSuccess) return fail(h, LDA_B200_ECUDA, "components failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -1070,8 +1126,8 @@ int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const in
         return 0;
     };
     if (!rc) rc = back();
-    free_corpus(c);
-    if (wc64) cudaFree(wc64);
+    free_corpus(h, c);
+    if (wc64) cudaFreeAsync(wc64, h->stream);
     return rc;
 }
 
