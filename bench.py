@@ -122,13 +122,13 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def committed_traffic(K):
+def committed_traffic(K, docs_per_launch):
     """dram bytes per launch of the minibatch kernel from the committed `ncu --set full` capture, if any"""
     path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(path):
         try:
             j = json.load(open(path))
-            if int(j.get("K", -1)) == K:
+            if int(j.get("K", -1)) == K and int(j.get("docs_per_launch", -1)) == docs_per_launch:
                 return j.get("dram_bytes_per_launch")
         except Exception:
             pass
@@ -295,7 +295,7 @@ def ours(args):
     roofline = {
         "bound": "hbm", "kernel": "scvb0_docs_kernel (fused burn-in + sufficient-statistics pass, one launch per minibatch)",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None,
-        "traffic": committed_traffic(K), "peak_source": peak_src,
+        "traffic": committed_traffic(K, b * args.processes_per_gpu), "peak_source": peak_src,
         "launches": mb_n.value, "avg_launch_ms": (mb_ms.value / mb_n.value) if mb_n.value else None,
         "algorithmic_bytes_per_launch": kbytes / mb_n.value if mb_n.value else None,
         "kernel_share_of_step": mb_ms.value / dev_ms if dev_ms else None,
