@@ -187,7 +187,7 @@ def reference_arm(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -276,7 +276,10 @@ def ours(args):
     import ctypes as C
     mb_ms, mb_n, bl_ms, bl_n = C.c_float(), C.c_int32(), C.c_float(), C.c_int32()
     L.lda_b200_last_kernel_time(h, C.byref(mb_ms), C.byref(mb_n), C.byref(bl_ms), C.byref(bl_n))
+    ar_ms, ar_n = C.c_float(), C.c_int32()
+    L.lda_b200_last_allreduce_time(h, C.byref(ar_ms), C.byref(ar_n))
     L.lda_b200_set_profiling(h, 0)
+    kernel_ms_max, kernel_ms_min = allmax(mb_ms.value), -allmax(-mb_ms.value)
     ms = allmax(dev_ms)
     wall_ms = allmax(wall_ms)
     total_launches = int(allsum(launches))
@@ -287,7 +290,6 @@ def ours(args):
     lda.FitIterate(1)
     perplexity = lda.PerplexityTrace[-1] if lda.PerplexityTrace else None
     lda.FitEnd(want_theta=False)
-    lda.Close()
 
     peak, peak_src = measured_peak()
     kbytes = alg_bytes(nnz_local, docs_local, K, B) * steps      # what this rank's minibatch kernels processed
@@ -301,6 +303,9 @@ def ours(args):
         "kernel_share_of_step": mb_ms.value / dev_ms if dev_ms else None,
         "blend_kernel": {"launches": bl_n.value, "avg_launch_ms": (bl_ms.value / bl_n.value) if bl_n.value else None,
                          "achieved_GBps": (16.0 * K * W * bl_n.value / (bl_ms.value * 1e-3) / 1e9) if bl_ms.value else None},
+        "allreduce": {"calls": ar_n.value, "avg_ms_incl_wait_for_slowest_rank": (ar_ms.value / ar_n.value) if ar_n.value else None,
+                      "bytes": 4 * K * W, "minibatch_kernel_ms_rank_min_max": [kernel_ms_min / max(mb_n.value, 1),
+                                                                                 kernel_ms_max / max(mb_n.value, 1)]},
         "whole_step_achieved_GBps": (alg_bytes(nnz, D, K, B) + bl_n.value / steps * 16.0 * K * W * world) * steps / (ms * 1e-3) / 1e9 / world,
     }
 
@@ -309,8 +314,12 @@ def ours(args):
     if not args.skip_e2e:
         out_t = torch.empty((K, D), dtype=torch.float64, pin_memory=True)   # page-locked result buffer
         out = out_t.numpy()
-        lda2 = new_lda(steps)
-        lda2._handle()
+        # the same model object a user would keep around (its communicator is already connected); a fresh RNG seed and
+        # fresh counters make it the same call as on a new object
+        lda2 = lda
+        lda2.Iterations, lda2.PerplexityEvaluationFrequency, lda2.PerplexityTolerance = steps, 30, 1e-2
+        lda2.Rnd = rand.New(rand.NewSource(0))
+        lda2.rhoPhiT, lda2.rhoThetaT, lda2.wordsInCorpus = 1.0, 1.0, 0.0
         barrier()
         t0 = time.perf_counter()
         lda2.FitTransform(m, out=out)
@@ -322,8 +331,8 @@ def ours(args):
         e2e = {"value": visits_per_step * K * steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d // steps,
                "d2h_bytes_per_step": d2h // steps, "seconds": t_e2e, "iterations": steps, "finite": ok,
                "call": "LatentDirichletAllocation.FitTransform(CSC host buffers) -> K x D float64"}
-        lda2.Close()
         del out
+    lda.Close()
 
     # ---- parity on a sample + CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------
     parity, cpu = None, None
@@ -333,6 +342,7 @@ def ours(args):
         sub = CSC(W, n_s, indptr[:n_s + 1].copy(), ind[:indptr[n_s]].copy(), data[:indptr[n_s]].copy())
         f = dict(Iterations=2, BatchSize=128, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0)
         a = new_lda(2)
+        a.Processes = 1      # deterministic mode: same minibatch order as the reference at Processes = 1
         o = O.LatentDirichletAllocation(K, seed=0)
         for k_, v_ in f.items():
             setattr(a, k_, v_)
@@ -365,13 +375,22 @@ def ours(args):
             "wall_ms_per_step": wall_ms / steps, "perplexity_after_%d_iterations" % (warmup + steps + 1): perplexity,
             "parity": parity,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+def _emit(line):
+    os.write(_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 if __name__ == "__main__":
+    # the contract is ONE JSON line on stdout: anything else a library prints there (e.g. NCCL's version banner) is
+    # sent to stderr by pointing fd 1 at fd 2 for the duration of the run; the JSON line goes to the saved fd
+    sys.stdout.flush()
+    _STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         reference_arm(a)

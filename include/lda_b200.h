@@ -187,6 +187,9 @@ int64_t lda_b200_launch_count(const lda_b200_handle *h);
 int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
                               float *blend_ms, int32_t *blend_launches);
 
+/* same for the per-step all-reduce (multi-GPU); the time includes waiting for the slowest rank's kernel */
+int lda_b200_last_allreduce_time(const lda_b200_handle *h, float *allreduce_ms, int32_t *allreduce_calls);
+
 #ifdef __cplusplus
 }
 #endif

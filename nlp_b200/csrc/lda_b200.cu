@@ -50,7 +50,7 @@ struct Corpus {
 
 struct EventPair {
     cudaEvent_t a, b;
-    int kind;  // 0 = minibatch kernel, 1 = blend kernel
+    int kind;  // 0 = minibatch kernel, 1 = blend kernel, 2 = all-reduce (includes waiting for the slowest rank)
 };
 
 }  // namespace
@@ -101,8 +101,8 @@ struct lda_b200_handle {
     bool profiling = false;
     std::vector<EventPair> ev_pool;
     size_t ev_used = 0;
-    float mb_ms = 0, blend_ms = 0;
-    int mb_n = 0, blend_n = 0;
+    float mb_ms = 0, blend_ms = 0, ar_ms = 0;
+    int mb_n = 0, blend_n = 0, ar_n = 0;
 };
 
 namespace {
@@ -300,17 +300,20 @@ int ev_end(lda_b200_handle *h, int slot) {
     return 0;
 }
 int ev_collect(lda_b200_handle *h) {
-    h->mb_ms = h->blend_ms = 0;
-    h->mb_n = h->blend_n = 0;
+    h->mb_ms = h->blend_ms = h->ar_ms = 0;
+    h->mb_n = h->blend_n = h->ar_n = 0;
     for (size_t i = 0; i < h->ev_used; ++i) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b));
         if (h->ev_pool[i].kind == 0) {
             h->mb_ms += ms;
             h->mb_n++;
-        } else {
+        } else if (h->ev_pool[i].kind == 1) {
             h->blend_ms += ms;
             h->blend_n++;
+        } else {
+            h->ar_ms += ms;
+            h->ar_n++;
         }
     }
     h->ev_used = 0;
@@ -865,8 +868,12 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 TRY(launch_docs<true>(h, a, c.order));
                 TRY(ev_end(h, slot));
             }
-            if (R > 1)
+            if (R > 1) {
+                int slot;
+                TRY(ev_begin(h, 2, &slot));
                 NC(nccl().AllReduce(h->nphi_hat, h->nphi_hat, (size_t)h->W * h->Kp, ncclFloat, ncclSum, h->comm, h->stream));
+                TRY(ev_end(h, slot));
+            }
             BlendArgs ba;
             ba.nphi = h->nphi;
             ba.nphi_hat = h->nphi_hat;
@@ -1140,6 +1147,13 @@ int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int
     if (minibatch_launches) *minibatch_launches = h->mb_n;
     if (blend_ms) *blend_ms = h->blend_ms;
     if (blend_launches) *blend_launches = h->blend_n;
+    return 0;
+}
+
+int lda_b200_last_allreduce_time(const lda_b200_handle *h, float *allreduce_ms, int32_t *allreduce_calls) {
+    if (!h) return LDA_B200_EINVAL;
+    if (allreduce_ms) *allreduce_ms = h->ar_ms;
+    if (allreduce_calls) *allreduce_calls = h->ar_n;
     return 0;
 }
 
