@@ -303,7 +303,8 @@ def ours(args):
         "kernel_share_of_step": mb_ms.value / dev_ms if dev_ms else None,
         "blend_kernel": {"launches": bl_n.value, "avg_launch_ms": (bl_ms.value / bl_n.value) if bl_n.value else None,
                          "achieved_GBps": (16.0 * K * W * bl_n.value / (bl_ms.value * 1e-3) / 1e9) if bl_ms.value else None},
-        "allreduce": {"calls": ar_n.value, "avg_ms_incl_wait_for_slowest_rank": (ar_ms.value / ar_n.value) if ar_n.value else None,
+        "allreduce": {"path": "peer-memory reduce+blend kernel (CUDA IPC over NVLink)" if lda.CommInfo()[2] else
+                      ("ncclAllReduce + blend kernel" if world > 1 else "none (1 GPU)"), "calls": ar_n.value, "avg_ms_incl_wait_for_slowest_rank": (ar_ms.value / ar_n.value) if ar_n.value else None,
                       "bytes": 4 * K * W, "minibatch_kernel_ms_rank_min_max": [kernel_ms_min / max(mb_n.value, 1),
                                                                                  kernel_ms_max / max(mb_n.value, 1)]},
         "whole_step_achieved_GBps": (alg_bytes(nnz, D, K, B) + bl_n.value / steps * 16.0 * K * W * world) * steps / (ms * 1e-3) / 1e9 / world,

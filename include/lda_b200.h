@@ -187,6 +187,10 @@ int64_t lda_b200_launch_count(const lda_b200_handle *h);
 int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
                               float *blend_ms, int32_t *blend_launches);
 
+/* which multi-GPU step path the last fit used: peer_memory_path = 1 when the reduction of nPhiHat and the M-step run
+ * as one kernel over NVLink peer memory (CUDA IPC), 0 when ncclAllReduce + blend is used (fallback, or
+ * LDA_B200_PEER_MEMORY=0) */
+int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks, int32_t *peer_memory_path);
 /* same for the per-step all-reduce (multi-GPU); the time includes waiting for the slowest rank's kernel */
 int lda_b200_last_allreduce_time(const lda_b200_handle *h, float *allreduce_ms, int32_t *allreduce_calls);
 

@@ -63,6 +63,7 @@ SYMBOLS = {
     "lda_b200_launch_count": (C.c_int64, [_P]),
     "lda_b200_last_kernel_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float),
                                             C.POINTER(C.c_int32)]),
+    "lda_b200_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lda_b200_last_allreduce_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 

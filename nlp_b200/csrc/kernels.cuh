@@ -555,6 +555,164 @@ __global__ void __launch_bounds__(256) phi_blend_kernel(const BlendArgs a) {
     }
 }
 
+// ---- multi-GPU: reduction over NVLink peer memory fused with the M-step ---------------------------------
+// Replaces ncclAllReduce(nPhiHat) + phi_blend_kernel.  Rank r owns the row slice [row0,row1): it loads that slice of
+// nPhiHat from every rank (peer loads, fixed rank order so that every element has one well-defined value), applies
+// nPhi' = A nPhi + C sum (lda.go:303-310), stores the new slice into EVERY rank's nPhi replica (peer stores), and
+// accumulates its partial column sums (nZHat, lda.go:295).  It also zeroes the local nPhiHat buffer of the next step
+// (two buffers alternate so that peers may still be reading the current one).  Cross-GPU ordering comes from the two
+// xgpu_barrier kernels that bracket it on the stream.
+constexpr int MAX_PEERS = 8;
+struct PeerTable {
+    float *hat[2][MAX_PEERS];      // nPhiHat ping-pong buffers of every rank
+    float *nphi[MAX_PEERS];        // nPhi replica of every rank
+    unsigned *flags[MAX_PEERS];    // [MAX_PEERS] arrival epochs, one array per rank
+    double *nzpart[MAX_PEERS];     // [MAX_PEERS][Kp] partial column sums, one array per rank
+    int rank, nranks;
+};
+
+struct FusedArgs {
+    PeerTable pt;
+    int cur;                 // which nPhiHat buffer holds this step's statistics
+    int64_t row0, row1, W;
+    int Kp;
+    float A, C;
+    double *nzhat_local;     // [Kp] this rank's partial column sums (zero on entry)
+};
+
+__global__ void __launch_bounds__(256) peer_reduce_blend_kernel(const FusedArgs a) {
+    extern __shared__ float4 sm4[];
+    const int R = a.pt.nranks, me = a.pt.rank;
+    const int VPR = a.Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = a.row0 + (int64_t)blockIdx.x * RPB + rslot; r < a.row1; r += (int64_t)gridDim.x * RPB) {
+        const int64_t e = r * VPR + col;  // float4 index
+        float4 h[MAX_PEERS];
+#pragma unroll
+        for (int q = 0; q < MAX_PEERS; ++q)
+            if (q < R) h[q] = reinterpret_cast<const float4 *>(a.pt.hat[a.cur][q])[e];  // all peer loads in flight
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < MAX_PEERS; ++q)
+            if (q < R) {
+                sum.x += h[q].x;
+                sum.y += h[q].y;
+                sum.z += h[q].z;
+                sum.w += h[q].w;
+            }
+        float4 p = reinterpret_cast<const float4 *>(a.pt.nphi[me])[e];
+        p.x = fmaf(a.A, p.x, a.C * sum.x);
+        p.y = fmaf(a.A, p.y, a.C * sum.y);
+        p.z = fmaf(a.A, p.z, a.C * sum.z);
+        p.w = fmaf(a.A, p.w, a.C * sum.w);
+#pragma unroll
+        for (int q = 0; q < MAX_PEERS; ++q)
+            if (q < R) reinterpret_cast<float4 *>(a.pt.nphi[q])[e] = p;
+        acc.x += sum.x;
+        acc.y += sum.y;
+        acc.z += sum.z;
+        acc.w += sum.w;
+    }
+    // zero the buffer the next step accumulates into (its readers finished at the previous step's closing barrier)
+    {
+        float4 *z = reinterpret_cast<float4 *>(a.pt.hat[a.cur ^ 1][me]);
+        const int64_t n4 = a.W * VPR;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    sm4[threadIdx.x] = acc;
+    __syncthreads();
+    if (rslot == 0) {
+        double sx = 0, sy = 0, sz = 0, sw = 0;
+        for (int s = 0; s < RPB; ++s) {
+            const float4 t = sm4[s * VPR + col];
+            sx += t.x;
+            sy += t.y;
+            sz += t.z;
+            sw += t.w;
+        }
+        atomicAdd(a.nzhat_local + 4 * col + 0, sx);
+        atomicAdd(a.nzhat_local + 4 * col + 1, sy);
+        atomicAdd(a.nzhat_local + 4 * col + 2, sz);
+        atomicAdd(a.nzhat_local + 4 * col + 3, sw);
+    }
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Cross-GPU barrier on the stream: one block, thread q talks to rank q.  Every rank writes `epoch` into slot `rank` of
+// every rank's flag array and waits until all slots of its own array reached `epoch`.  The wait is bounded (every rank
+// launches the same kernel sequence, so the peers arrive within microseconds); on expiry *err is set instead of
+// hanging the GPU.
+// FINISH additionally publishes this rank's partial column sums before signalling, and after the wait completes the
+// M-step for nZ (lda.go:313-317): nZ = A nZ + C sum_q part_q (fixed rank order), invZ, and resets the schedulers.
+struct BarrierArgs {
+    PeerTable pt;
+    unsigned epoch;
+    int finish;
+    int K, Kp;
+    double *nzhat_local;
+    double *nz;
+    float *inv_z;
+    double Ad, Cd, etaW;
+    unsigned *ticket;
+    int *doc_counter;
+    int *err;
+};
+
+__global__ void __launch_bounds__(256) xgpu_barrier_kernel(const BarrierArgs a) {
+    const int R = a.pt.nranks, me = a.pt.rank;
+    if (a.finish) {
+        for (int k = threadIdx.x; k < a.Kp; k += blockDim.x) {
+            const double v = a.nzhat_local[k];
+            for (int q = 0; q < R; ++q) a.pt.nzpart[q][me * a.Kp + k] = v;
+            a.nzhat_local[k] = 0.0;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if ((int)threadIdx.x < R) {
+        st_release_sys(a.pt.flags[threadIdx.x] + me, a.epoch);
+        const unsigned *mine = a.pt.flags[me] + threadIdx.x;
+        long long spins = 0;
+        while ((int)(ld_acquire_sys(mine) - a.epoch) < 0) {
+            if (++spins > (1LL << 24)) {
+                *a.err = 2;
+                break;
+            }
+            __nanosleep(64);
+        }
+    }
+    __syncthreads();
+    if (a.finish) {
+        for (int k = threadIdx.x; k < a.Kp; k += blockDim.x) {
+            if (k < a.K) {
+                double sum = 0.0;
+                for (int q = 0; q < R; ++q) sum += a.pt.nzpart[me][q * a.Kp + k];
+                const double z = a.Ad * a.nz[k] + a.Cd * sum;
+                a.nz[k] = z;
+                a.inv_z[k] = (float)(1.0 / (z + a.etaW));
+            } else {
+                a.inv_z[k] = 0.f;
+            }
+        }
+        if (threadIdx.x == 0) {
+            *a.ticket = 0u;
+            *a.doc_counter = 0;
+        }
+    }
+}
+
 // invZ from nZ (after init / set_state)
 __global__ void inv_z_kernel(const double *nz, float *inv_z, int K, int Kp, double etaW) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;

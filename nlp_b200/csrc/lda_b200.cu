@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <string>
@@ -95,6 +96,18 @@ struct lda_b200_handle {
     // comm
     ncclComm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory path (fused reduction + M-step over NVLink); falls back to ncclAllReduce + blend when unavailable
+    bool peer_ok = false;
+    bool peer_wanted = true;
+    PeerTable peers;
+    float *hat_buf[2] = {nullptr, nullptr};  // cudaMalloc'ed (IPC-capable) nPhiHat ping-pong buffers
+    float *nphi_ipc = nullptr;               // cudaMalloc'ed nPhi when peers map it
+    unsigned *peer_flags = nullptr;
+    double *peer_nzpart = nullptr;
+    std::vector<void *> ipc_opened;
+    unsigned epoch = 0;
+    int hat_cur = 0;
+    std::string peer_note;
 
     // stats
     int64_t launches = 0;
@@ -320,12 +333,15 @@ int ev_collect(lda_b200_handle *h) {
     return 0;
 }
 
+void peer_teardown(lda_b200_handle *h);
+
 // ---- model allocation -------------------------------------------------------------------------------
 int ensure_model(lda_b200_handle *h, int64_t W) {
     const int K = h->cfg.K, Kp = (K + 3) & ~3;
     if (h->W == W && h->K == K && h->nphi) return 0;
     if (W < 1) return fail(h, LDA_B200_EINVAL, "matrix has no rows (W = %lld)", (long long)W);
     if (W > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "W = %lld exceeds int32 word ids", (long long)W);
+    peer_teardown(h);
     h->W = W;
     h->K = K;
     h->Kp = Kp;
@@ -340,6 +356,147 @@ int ensure_model(lda_b200_handle *h, int64_t W) {
     CU(cudaMemsetAsync(h->nphi_hat, 0, (size_t)W * Kp * sizeof(float), h->stream));
     CU(cudaMemsetAsync(h->nzhat, 0, (size_t)Kp * sizeof(double), h->stream));
     CU(cudaMemsetAsync(h->nz, 0, (size_t)Kp * sizeof(double), h->stream));
+    return 0;
+}
+
+// ---- peer-memory setup ------------------------------------------------------------------------------------------
+struct PeerRec {
+    int pid, dev;
+    cudaIpcMemHandle_t mh[5];  // hat0, hat1, nphi, flags, nzpart
+    void *ptr[5];
+};
+
+void peer_teardown(lda_b200_handle *h) {
+    for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
+    h->ipc_opened.clear();
+    if (h->peer_ok || h->hat_buf[0]) {
+        // the model buffers were plain cudaMalloc allocations shared with the peers
+        if (h->nphi_ipc) {
+            cudaFree(h->nphi_ipc);
+            if (h->nphi == h->nphi_ipc) h->nphi = nullptr;
+            h->nphi_ipc = nullptr;
+        }
+        for (int i = 0; i < 2; ++i) {
+            if (h->hat_buf[i]) cudaFree(h->hat_buf[i]);
+            if (h->nphi_hat == h->hat_buf[i]) h->nphi_hat = nullptr;
+            h->hat_buf[i] = nullptr;
+        }
+        if (h->peer_flags) cudaFree(h->peer_flags);
+        if (h->peer_nzpart) cudaFree(h->peer_nzpart);
+        h->peer_flags = nullptr;
+        h->peer_nzpart = nullptr;
+    }
+    h->peer_ok = false;
+}
+
+// Allocates the shared model buffers with cudaMalloc, exchanges their CUDA IPC handles with every rank through an
+// ncclAllGather, and maps the peers' buffers.  Any failure leaves peer_ok = false (NCCL all-reduce path).
+int peer_setup(lda_b200_handle *h) {
+    const int R = h->nranks;
+    h->peer_ok = false;
+    h->peer_note.clear();
+    if (R <= 1 || !h->peer_wanted) return 0;
+    if (R > MAX_PEERS) {
+        h->peer_note = "more than 8 ranks";
+        return 0;
+    }
+    const size_t n = (size_t)h->W * h->Kp;
+    auto soft = [&](cudaError_t e, const char *what) -> bool {
+        if (e == cudaSuccess) return true;
+        h->peer_note = std::string(what) + ": " + cudaGetErrorString(e);
+        cudaGetLastError();
+        return false;
+    };
+    PeerRec mine;
+    memset(&mine, 0, sizeof mine);
+    mine.pid = (int)getpid();
+    mine.dev = h->device;
+    bool ok = soft(cudaMalloc((void **)&h->hat_buf[0], n * sizeof(float)), "cudaMalloc") &&
+              soft(cudaMalloc((void **)&h->hat_buf[1], n * sizeof(float)), "cudaMalloc") &&
+              soft(cudaMalloc((void **)&h->nphi_ipc, n * sizeof(float)), "cudaMalloc") &&
+              soft(cudaMalloc((void **)&h->peer_flags, MAX_PEERS * sizeof(unsigned)), "cudaMalloc") &&
+              soft(cudaMalloc((void **)&h->peer_nzpart, (size_t)MAX_PEERS * h->Kp * sizeof(double)), "cudaMalloc");
+    void *bufs[5] = {h->hat_buf[0], h->hat_buf[1], h->nphi_ipc, h->peer_flags, h->peer_nzpart};
+    if (ok) {
+        CU(cudaMemsetAsync(h->hat_buf[0], 0, n * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->hat_buf[1], 0, n * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->peer_flags, 0, MAX_PEERS * sizeof(unsigned), h->stream));
+        CU(cudaMemsetAsync(h->peer_nzpart, 0, (size_t)MAX_PEERS * h->Kp * sizeof(double), h->stream));
+        for (int i = 0; i < 5 && ok; ++i) {
+            mine.ptr[i] = bufs[i];
+            ok = soft(cudaIpcGetMemHandle(&mine.mh[i], bufs[i]), "cudaIpcGetMemHandle");
+        }
+    }
+    if (!ok) mine.pid = -1;  // tell the peers this rank cannot take part
+    // exchange the records (every rank must reach this point, successful or not)
+    PeerRec *drec = nullptr;
+    TRY(dalloc(h, &drec, (size_t)R));
+    CU(cudaMemcpyAsync(drec + h->rank, &mine, sizeof mine, cudaMemcpyHostToDevice, h->stream));
+    NC(nccl().AllGather(drec + h->rank, drec, sizeof(PeerRec), ncclChar, h->comm, h->stream));
+    std::vector<PeerRec> all((size_t)R);
+    CU(cudaMemcpyAsync(all.data(), drec, sizeof(PeerRec) * (size_t)R, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, &drec);
+    for (int q = 0; q < R; ++q)
+        if (all[(size_t)q].pid < 0) ok = false;
+    PeerTable t;
+    memset(&t, 0, sizeof t);
+    t.rank = h->rank;
+    t.nranks = R;
+    for (int q = 0; q < R && ok; ++q) {
+        void *p[5];
+        for (int i = 0; i < 5 && ok; ++i) {
+            if (q == h->rank) {
+                p[i] = bufs[i];
+            } else if (all[(size_t)q].pid == mine.pid) {
+                // same process (e.g. one goroutine per GPU): plain peer access, no IPC
+                int can = 0;
+                ok = soft(cudaDeviceCanAccessPeer(&can, h->device, all[(size_t)q].dev), "cudaDeviceCanAccessPeer") && can;
+                if (ok) {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(all[(size_t)q].dev, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) {
+                        cudaGetLastError();
+                        e = cudaSuccess;
+                    }
+                    ok = soft(e, "cudaDeviceEnablePeerAccess");
+                }
+                p[i] = all[(size_t)q].ptr[i];
+            } else {
+                ok = soft(cudaIpcOpenMemHandle(&p[i], all[(size_t)q].mh[i], cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+                if (ok) h->ipc_opened.push_back(p[i]);
+            }
+        }
+        if (!ok) break;
+        t.hat[0][q] = (float *)p[0];
+        t.hat[1][q] = (float *)p[1];
+        t.nphi[q] = (float *)p[2];
+        t.flags[q] = (unsigned *)p[3];
+        t.nzpart[q] = (double *)p[4];
+    }
+    // agreement: one rank failing to map a peer must switch everybody to the fallback
+    int *dflag = nullptr;
+    TRY(dalloc(h, &dflag, 1));
+    const int my_ok = ok ? 0 : 1;
+    CU(cudaMemcpyAsync(dflag, &my_ok, sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    NC(nccl().AllReduce(dflag, dflag, 1, ncclInt, ncclSum, h->comm, h->stream));
+    int bad = 0;
+    CU(cudaMemcpyAsync(&bad, dflag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, &dflag);
+    if (bad) {
+        if (h->peer_note.empty()) h->peer_note = "a peer could not map the shared buffers";
+        peer_teardown(h);
+        return 0;
+    }
+    // switch the model over to the shared buffers
+    dfree(h, &h->nphi);
+    dfree(h, &h->nphi_hat);
+    h->nphi = h->nphi_ipc;
+    h->nphi_hat = h->hat_buf[0];
+    h->peers = t;
+    h->hat_cur = 0;
+    h->epoch = 0;
+    h->peer_ok = true;
     return 0;
 }
 
@@ -694,6 +851,7 @@ void lda_b200_destroy(lda_b200_handle *h) {
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    peer_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
     free_corpus(h, h->fitc);
     dfree(h, &h->nphi);
@@ -749,6 +907,7 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
     if (nranks < 1 || rank < 0 || rank >= nranks) return fail(h, LDA_B200_EINVAL, "bad rank %d of %d", rank, nranks);
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
+    peer_teardown(h);
     if (h->comm) {
         nccl().CommDestroy(h->comm);
         h->comm = nullptr;
@@ -763,6 +922,8 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
     NC(nccl().CommInitRank(&h->comm, nranks, id, rank));
     h->rank = rank;
     h->nranks = nranks;
+    const char *env = getenv("LDA_B200_PEER_MEMORY");  // "0" forces the ncclAllReduce + blend path
+    h->peer_wanted = !(env && env[0] == '0');
     return 0;
 }
 
@@ -779,6 +940,7 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     // init (lda.go:193-206): nPhi/nZ are re-allocated on every fit, no warm start
     h->W = 0;
     TRY(ensure_model(h, W));
+    TRY(peer_setup(h));
     uint64_t draws = 0;
     if (nphi0) {
         std::vector<Segment> all{{0, W, 0}};
@@ -868,34 +1030,79 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 TRY(launch_docs<true>(h, a, c.order));
                 TRY(ev_end(h, slot));
             }
-            if (R > 1) {
+            const double Ad = A, Cd = (n_s > 1) ? 1.0 : c_single;
+            if (h->peer_ok) {
+                // fused path: [barrier] -> reduce over peer memory + M-step on this rank's row slice -> [barrier + nZ]
+                BarrierArgs bar;
+                bar.pt = h->peers;
+                bar.finish = 0;
+                bar.K = h->K;
+                bar.Kp = h->Kp;
+                bar.nzhat_local = h->nzhat;
+                bar.nz = h->nz;
+                bar.inv_z = h->inv_z;
+                bar.Ad = Ad;
+                bar.Cd = Cd;
+                bar.etaW = cfg.eta * (double)h->W;
+                bar.ticket = h->ticket;
+                bar.doc_counter = h->doc_counter;
+                bar.err = h->err_flag;
                 int slot;
                 TRY(ev_begin(h, 2, &slot));
-                NC(nccl().AllReduce(h->nphi_hat, h->nphi_hat, (size_t)h->W * h->Kp, ncclFloat, ncclSum, h->comm, h->stream));
+                bar.epoch = ++h->epoch;
+                xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
+                KCHECK();
+                FusedArgs fa;
+                fa.pt = h->peers;
+                fa.cur = h->hat_cur;
+                const int64_t rows_per = (h->W + R - 1) / R;
+                fa.row0 = std::min<int64_t>(h->W, rows_per * h->rank);
+                fa.row1 = std::min<int64_t>(h->W, fa.row0 + rows_per);
+                fa.W = h->W;
+                fa.Kp = h->Kp;
+                fa.A = (float)Ad;
+                fa.C = (float)Cd;
+                fa.nzhat_local = h->nzhat;
+                const int bs = blend_block(h->Kp);
+                peer_reduce_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                KCHECK();
+                bar.finish = 1;
+                bar.epoch = ++h->epoch;
+                xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
+                KCHECK();
+                TRY(ev_end(h, slot));
+                h->hat_cur ^= 1;
+                h->nphi_hat = h->hat_buf[h->hat_cur];
+            } else {
+                if (R > 1) {
+                    int slot;
+                    TRY(ev_begin(h, 2, &slot));
+                    NC(nccl().AllReduce(h->nphi_hat, h->nphi_hat, (size_t)h->W * h->Kp, ncclFloat, ncclSum, h->comm, h->stream));
+                    TRY(ev_end(h, slot));
+                }
+                BlendArgs ba;
+                ba.nphi = h->nphi;
+                ba.nphi_hat = h->nphi_hat;
+                ba.nz = h->nz;
+                ba.nzhat = h->nzhat;
+                ba.inv_z = h->inv_z;
+                ba.ticket = h->ticket;
+                ba.doc_counter = h->doc_counter;
+                ba.W = h->W;
+                ba.K = h->K;
+                ba.Kp = h->Kp;
+                ba.Ad = Ad;
+                ba.Cd = Cd;
+                ba.A = (float)ba.Ad;
+                ba.C = (float)ba.Cd;
+                ba.etaW = cfg.eta * (double)h->W;
+                const int bs = blend_block(h->Kp);
+                int slot;
+                TRY(ev_begin(h, 1, &slot));
+                phi_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(ba);
+                KCHECK();
                 TRY(ev_end(h, slot));
             }
-            BlendArgs ba;
-            ba.nphi = h->nphi;
-            ba.nphi_hat = h->nphi_hat;
-            ba.nz = h->nz;
-            ba.nzhat = h->nzhat;
-            ba.inv_z = h->inv_z;
-            ba.ticket = h->ticket;
-            ba.doc_counter = h->doc_counter;
-            ba.W = h->W;
-            ba.K = h->K;
-            ba.Kp = h->Kp;
-            ba.Ad = A;
-            ba.Cd = (n_s > 1) ? 1.0 : c_single;
-            ba.A = (float)ba.Ad;
-            ba.C = (float)ba.Cd;
-            ba.etaW = cfg.eta * (double)h->W;
-            const int bs = blend_block(h->Kp);
-            int slot;
-            TRY(ev_begin(h, 1, &slot));
-            phi_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(ba);
-            KCHECK();
-            TRY(ev_end(h, slot));
             ctr->rho_phi_t += n_s;  // lda.go:300
         }
         h->it_done++;
@@ -921,6 +1128,11 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
         cudaEventDestroy(e1);
     } else {
         CU(cudaStreamSynchronize(h->stream));
+    }
+    if (h->peer_ok) {
+        int bad = 0;
+        CU(cudaMemcpy(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost));
+        if (bad == 2) return fail(h, LDA_B200_ENCCL, "a cross-GPU barrier timed out (a peer rank did not arrive)");
     }
     if (h->profiling) TRY(ev_collect(h));
     if (n_evals) *n_evals = evals;
@@ -1147,6 +1359,14 @@ int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int
     if (minibatch_launches) *minibatch_launches = h->mb_n;
     if (blend_ms) *blend_ms = h->blend_ms;
     if (blend_launches) *blend_launches = h->blend_n;
+    return 0;
+}
+
+int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks, int32_t *peer_memory_path) {
+    if (!h) return LDA_B200_EINVAL;
+    if (rank) *rank = h->rank;
+    if (nranks) *nranks = h->nranks;
+    if (peer_memory_path) *peer_memory_path = h->peer_ok ? 1 : 0;
     return 0;
 }
 

@@ -141,6 +141,14 @@ class LatentDirichletAllocation:
             _lib.check(L.lda_b200_comm_init(self._h, 0, 1, None), self._h)
         self._comm_ranks = nranks
 
+    def CommInfo(self):
+        """(rank, ranks, peer_memory_path) of the handle's communicator; peer_memory_path is True when the multi-GPU
+        step runs as one reduce + M-step kernel over NVLink peer memory instead of ncclAllReduce + blend"""
+        r, n, p = C.c_int32(0), C.c_int32(1), C.c_int32(0)
+        if self._h is not None:
+            _lib.lib().lda_b200_comm_info(self._h, C.byref(r), C.byref(n), C.byref(p))
+        return r.value, n.value, bool(p.value)
+
     def Close(self):
         if self._h is not None:
             _lib.lib().lda_b200_destroy(self._h)

@@ -20,9 +20,10 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, ret):
+def _worker(rank, world, port, case, peer, ret):
     sys.path.insert(0, ROOT)
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank),
+                      LDA_B200_PEER_MEMORY="1" if peer else "0")
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -49,6 +50,7 @@ def _worker(rank, world, port, case, ret):
         lda.BatchSize, lda.Iterations = b, iters
         lda.PerplexityEvaluationFrequency, lda.PerplexityTolerance = 1, 0.0
         theta = lda.FitTransform(m)
+        assert lda.CommInfo() == (rank, world, peer), lda.CommInfo()
         nphi, nz = lda.GetState()
         held = corpus_synth.generate(3 * b + 7, W, seed=99, block=b, mean_distinct=40, n_topics=16)
         t, passes = lda.Transform(CSC(W, 3 * b + 7, *held), return_passes=True)
@@ -60,8 +62,11 @@ def _worker(rank, world, port, case, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl-allreduce"])
 @pytest.mark.parametrize("case", [(700, 600, 12, 64, 5), (1030, 800, 256, 128, 3)])
-def test_two_gpu_fit_matches_sync_group_oracle(case):
+def test_two_gpu_fit_matches_sync_group_oracle(case, peer):
+    """peer=True: reduction + M-step fused in one kernel over NVLink peer memory (CUDA IPC); peer=False: the
+    ncclAllReduce + blend fallback.  Both must give the same model."""
     import torch
     import torch.multiprocessing as mp
     if torch.cuda.device_count() < 2:
@@ -70,7 +75,7 @@ def test_two_gpu_fit_matches_sync_group_oracle(case):
     from oracle import oracle as O
     D, W, K, b, iters = case
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), case, ret), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), case, peer, ret), nprocs=2, join=True)
     r0, r1 = ret[0], ret[1]
 
     indptr, ind, data = corpus_synth.generate(D, W, block=b, mean_distinct=40, n_topics=16)
