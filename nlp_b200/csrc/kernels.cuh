@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace ldab {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -262,6 +264,7 @@ __device__ __forceinline__ void cp_async_wait() {
 struct Tile {
     int wi;   // word id of the token this lane holds (0 for padding)
     float q;  // 1-(1-rho)^v of that token (0 for padding)
+    int la;   // word id of the token R positions further down the document's token stream (-1: past the end)
 };
 
 constexpr int docs32_ring_rows(int NV) { return NV == 1 ? 8 : NV == 2 ? 6 : NV == 4 ? 4 : 3; }
@@ -276,8 +279,11 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     const int lane = threadIdx.x & 31;
     float4 *ring = ring_all + (threadIdx.x >> 5) * (R * NV * 32) + lane;  // slot s, slice v: ring[(s*NV+v)*32]
     const int Kp = FULLK ? 128 * NV : a.Kp;
+    const unsigned row_bytes = 4u * (unsigned)Kp;   // W*Kp*4 < 2^32 is checked by the host
+    unsigned lane_bytes = 16u * (unsigned)lane;
+    asm volatile("" : "+r"(lane_bytes));  // keep it in a register: ptxas otherwise re-derives it from %tid per token
     const float alpha = a.alpha, eta = a.eta;
-    const float *__restrict__ nphi = a.nphi + 4 * lane;
+    const char *__restrict__ nphi_b = reinterpret_cast<const char *>(a.nphi);
     const int32_t *__restrict__ ind = a.ind;
     const float *__restrict__ val = a.val;
     const float *__restrict__ tab = a.log1m_rho;
@@ -295,9 +301,10 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     // asynchronous copy of this lane's slices of row w into ring slot `slot`; always closes one cp.async group
     auto issue = [&](int slot, int w) {
         if (w >= 0) {
+            const char *src = nphi_b + ((unsigned)w * row_bytes + lane_bytes);
 #pragma unroll
             for (int v = 0; v < NV; ++v)
-                if (ok[v]) cp_async16(ring + (slot * NV + v) * 32, nphi + (int64_t)w * Kp + 128 * v);
+                if (ok[v]) cp_async16(ring + (slot * NV + v) * 32, reinterpret_cast<const float *>(src + 512 * v));
         }
         cp_async_commit();
     };
@@ -324,15 +331,27 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
             tha[v] = make_float4(t.x + alpha, t.y + alpha, t.z + alpha, t.w + alpha);
         }
         const int n_tiles = (len + 31) >> 5;
+        const int32_t *dind = ind + base;
+        const float *dval = val + base;
+        // word id at `ahead` positions past token (pass pi, index idx) of the document's token stream
+        auto stream_word = [&](int pi, int idx) -> int {
+            if (idx >= len) {
+                pi += idx / len;
+                idx %= len;
+            }
+            return pi < total_passes ? dind[idx] : -1;
+        };
         auto load_tile = [&](int pi, int ti) -> Tile {
             const int my = (ti << 5) + lane;
             Tile t;
             if (my < len) {
-                t.wi = ind[base + my];
-                t.q = -expm1f(val[base + my] * tab[min(pi + 1, passes)]);  // lda.go:231 / :274
+                t.wi = dind[my];
+                t.q = -expm1f(dval[my] * tab[min(pi + 1, passes)]);  // lda.go:231 / :274
+                t.la = stream_word(pi, my + R);
             } else {
                 t.wi = 0;
                 t.q = 0.f;
+                t.la = -1;
             }
             return t;
         };
@@ -343,24 +362,9 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                 if (ok[v]) s += ((double)(tha[v].x - alpha) + (tha[v].y - alpha)) + ((double)(tha[v].z - alpha) + (tha[v].w - alpha));
             return group_sum_d<32>(s);
         };
-
-        // look-ahead cursor: position of the next row to request = (pass la_pass, token la_idx); la_w is its word id
-        int la_idx, la_pass, la_w, slot;
-        auto la_advance = [&]() {
-            if (++la_idx == len) {
-                la_idx = 0;
-                ++la_pass;
-            }
-            la_w = la_pass < total_passes ? ind[base + la_idx] : -1;
-        };
-        auto prime = [&](int first_pass) {
-            la_idx = 0;
-            la_pass = first_pass;
-            la_w = ind[base];
-            for (int s = 0; s < R; ++s) {
-                issue(s, la_w);
-                la_advance();
-            }
+        int slot;
+        auto prime = [&](int first_pass) {  // request the rows of the first R stream positions from (first_pass, 0)
+            for (int s = 0; s < R; ++s) issue(s, stream_word(first_pass, s));
             slot = 0;
         };
 
@@ -375,6 +379,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
             Tile nxt;
             nxt.wi = 0;
             nxt.q = 0.f;
+            nxt.la = -1;
             if (has_next) nxt = load_tile(npi, nti);
             const int counter = pi + 1;
             const bool burn = pi < passes;
@@ -382,9 +387,11 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
             if (ti == 0 && chk && 1 < passes) prev = theta_sum();  // lda.go:224-230
 
             const int ntile = min(32, len - (ti << 5));
-            const bool main_pass = FIT && !burn;
+            auto run_tile = [&](auto is_main) {
+            constexpr bool MAINP = decltype(is_main)::value;
             for (int t = 0; t < ntile; ++t) {
                 const float qt = __shfl_sync(FULL, cur.q, t);
+                const int wn = __shfl_sync(FULL, cur.la, t);
                 cp_async_wait<R - 1>();  // the oldest outstanding group (this token's row) has landed
                 float4 c[NV];
 #pragma unroll
@@ -402,8 +409,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                         c[v].w = (row.w + eta) * iz[v].w;
                     }
                 }
-                issue(slot, la_w);  // refill the slot just consumed with the row R positions ahead
-                la_advance();
+                issue(slot, wn);  // refill the slot just consumed with the row R positions ahead
                 slot = slot + 1 == R ? 0 : slot + 1;
 
                 float p0 = 0.f, p1 = 0.f;
@@ -418,10 +424,10 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                 const float keep = 1.0f - qt;
                 const float mix = qt * wcj * r;
                 const float aq = alpha * qt;
-                if (FIT && main_pass) {
+                if (MAINP) {
                     const int w = __shfl_sync(FULL, cur.wi, t);
                     const float sc = hat_scale * r;
-                    float *hp = a.nphi_hat + (int64_t)w * Kp + 4 * lane;
+                    float *hp = reinterpret_cast<float *>(reinterpret_cast<char *>(a.nphi_hat) + ((unsigned)w * row_bytes + lane_bytes));
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
                         if (ok[v])
@@ -436,6 +442,11 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                     tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
                 }
             }
+            };
+            if (FIT && !burn)
+                run_tile(std::true_type{});
+            else
+                run_tile(std::false_type{});
             if (last_tile) {
                 if (burn) executed = counter;
                 if (chk && counter < passes) {  // lda.go:251-259
