@@ -130,6 +130,15 @@ int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr
                  lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
                  int32_t *iters_run);
 
+/* PartialFit: the OnlineTransformer method (vectorisers.go:36-39) the reference lists as a TODO for LDA
+ * (lda.go:147).  Runs `iterations` SCVB0 iterations (lda.go:501-528) over the given documents starting from the
+ * current nPhi / nZ / rhoPhiT; on a handle without a model it first draws nPhi like lda.go:193-206 (so one call on a
+ * fresh handle equals lda_b200_fit with Iterations = iterations and no perplexity evaluation).  nTheta of the given
+ * documents is drawn / taken from ntheta0 as in lda_b200_fit; wordsInCorpus accumulates (lda.go:481). */
+int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                         const double *data, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                         int32_t iterations, double *theta_out);
+
 /* Transform, lda.go:446-453 (unNormalisedTransform lda.go:420-437 + normaliseTheta).
  *  theta0  D*K values [j*K+k] replacing the draws of lda.go:422-426, or NULL (then *rnd)
  *  rho_theta_t  the model's current rhoThetaT (burnInDoc uses it, lda.go:231)

@@ -44,6 +44,8 @@ SYMBOLS = {
     "lda_b200_plan_shard": (C.c_int64, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int64]),
     "lda_b200_fit": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters), _P, _P,
                                C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "lda_b200_partial_fit": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters),
+                                       C.c_int32, _P]),
     "lda_b200_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, _P, _P]),
     "lda_b200_perplexity": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, C.POINTER(C.c_double)]),
     "lda_b200_components": (C.c_int, [_P, _P]),

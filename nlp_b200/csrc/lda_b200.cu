@@ -930,21 +930,39 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
 }
 
 // ---- FitTransform, lda.go:463-542 ----------------------------------------------------------------------
-int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                       const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
-                       lda_b200_counters *ctr) {
+static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                          const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                          lda_b200_counters *ctr, bool warm) {
     if (!h) return LDA_B200_EINVAL;
     if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
-    if ((!nphi0 || !ntheta0) && !rnd) return fail(h, LDA_B200_EINVAL, "neither initial values nor a PCG state were given");
+    if (warm && (!h->fitted || h->W != W))
+        return fail(h, LDA_B200_ESTATE, "PartialFit on a fitted model needs the same number of rows (have %lld, got %lld)",
+                    (long long)h->W, (long long)W);
+    if (((!nphi0 && !warm) || !ntheta0) && !rnd) return fail(h, LDA_B200_EINVAL, "neither initial values nor a PCG state were given");
     CU(cudaSetDevice(h->device));
     PhaseTimer pt(h->stream);
     h->fit_open = false;
-    // init (lda.go:193-206): nPhi/nZ are re-allocated on every fit, no warm start
-    h->W = 0;
-    TRY(ensure_model(h, W));
-    TRY(peer_setup(h));
+    // init (lda.go:193-206): nPhi/nZ are re-initialised on every fit, no warm start.  The device buffers (and the
+    // peer mappings) are kept when the shape is unchanged; every value in them is rewritten below.
+    const bool same_shape = h->nphi && h->W == W && h->K == h->cfg.K && (h->nranks == 1 || h->peer_ok || !h->peer_wanted);
+    if (warm && !same_shape) {
+        // keep the model values while moving them into peer-shared buffers: not needed on one GPU, unsupported here
+        return fail(h, LDA_B200_EUNSUPPORTED, "PartialFit across a communicator change is not supported");
+    }
+    if (!same_shape) {
+        h->W = 0;
+        TRY(ensure_model(h, W));
+        TRY(peer_setup(h));
+    }
+    if (h->peer_ok) {
+        CU(cudaMemsetAsync(h->hat_buf[0], 0, (size_t)W * h->Kp * sizeof(float), h->stream));
+        CU(cudaMemsetAsync(h->hat_buf[1], 0, (size_t)W * h->Kp * sizeof(float), h->stream));
+    }
+    CU(cudaMemsetAsync(h->nzhat, 0, (size_t)h->Kp * sizeof(double), h->stream));
     uint64_t draws = 0;
-    if (nphi0) {
+    if (warm) {
+        // streaming step: nPhi / nZ / rhoPhiT carry over
+    } else if (nphi0) {
         std::vector<Segment> all{{0, W, 0}};
         TRY(upload_rows(h, all, nphi0, h->K, h->Kp, h->nphi));
     } else {
@@ -954,7 +972,7 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
         KCHECK();
         draws += (uint64_t)W * (uint64_t)h->K;
     }
-    TRY(refresh_nz_from_nphi(h));
+    if (!warm) TRY(refresh_nz_from_nphi(h));
     TRY(refresh_inv_z(h));
     pt.lap("fit_begin: model alloc + nPhi init");
 
@@ -966,7 +984,7 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     if (rnd && draws) advance(rnd, draws);
 
     ctr->words_in_corpus += h->fitc.n_global;  // lda.go:481 (never reset)
-    ctr->rho_phi_t = 1;                        // lda.go:497
+    if (!warm) ctr->rho_phi_t = 1;             // lda.go:497
     CU(cudaMemsetAsync(h->nphi_hat, 0, (size_t)h->W * h->Kp * sizeof(float), h->stream));
     CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
     CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
@@ -976,6 +994,34 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
     h->fit_open = true;
     h->fitted = true;
     return 0;
+}
+
+int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                       const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                       lda_b200_counters *ctr) {
+    return fit_begin_impl(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr, false);
+}
+
+// PartialFit (OnlineTransformer, vectorisers.go:36-39; a TODO for LDA at lda.go:147): `iterations` SCVB0 iterations
+// over the given documents starting from the current nPhi / nZ / rhoPhiT (from a fresh random model on first use).
+int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                         const double *data, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                         int32_t iterations, double *theta_out) {
+    if (!h) return LDA_B200_EINVAL;
+    const bool warm = h->fitted;
+    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nullptr, ntheta0, rnd, ctr, warm));
+    const int32_t saved_it = h->cfg.iterations, saved_f = h->cfg.perplexity_evaluation_frequency;
+    h->cfg.iterations = iterations;
+    h->cfg.perplexity_evaluation_frequency = 0;
+    int rc = lda_b200_fit_iterate(h, iterations, ctr, nullptr, 0, nullptr, nullptr, nullptr, nullptr);
+    h->cfg.iterations = saved_it;
+    h->cfg.perplexity_evaluation_frequency = saved_f;
+    if (rc) {
+        free_corpus(h, h->fitc);
+        h->fit_open = false;
+        return rc;
+    }
+    return lda_b200_fit_end(h, theta_out);
 }
 
 int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_counters *ctr, double *perp_trace,

@@ -89,6 +89,7 @@ class LatentDirichletAllocation:
         self.IterationsRun = 0
         self._h = None
         self._comm_ranks = 1
+        self._has_model = False
 
     # ---- handle management ------------------------------------------------------------------------------
     def _config(self):
@@ -183,7 +184,6 @@ class LatentDirichletAllocation:
         csc = as_csc(m)
         h = self._handle()
         L = _lib.lib()
-        self.w, self.d = csc.rows, csc.cols
         if not self.DeviceInit:
             if nphi0 is None:
                 nphi0 = self._draws(csc.rows, csc.rows * self.K)
@@ -208,9 +208,11 @@ class LatentDirichletAllocation:
                             _ptr(ntheta0), self.Rnd.src._s, ctr, _ptr(theta), _ptr(trace), cap, C.byref(n_evals),
                             C.byref(iters))
         _lib.check(rc, h)
+        self.w, self.d = csc.rows, csc.cols
         self._take(ctr)
         self.PerplexityTrace = trace[:n_evals.value].tolist()
         self.IterationsRun = iters.value
+        self._has_model = True
         return theta
 
     # ---- resident-corpus stepping (not in the reference; lda_b200_fit is exactly these three calls) -------------
@@ -218,7 +220,6 @@ class LatentDirichletAllocation:
         """ingest + init of lda.go:464-497; the corpus stays in HBM until FitEnd"""
         csc = as_csc(m)
         h = self._handle()
-        self.w, self.d = csc.rows, csc.cols
         if not self.DeviceInit:
             nphi0 = self._draws(csc.rows, csc.rows * self.K) if nphi0 is None else nphi0
             ntheta0 = self._draws(csc.cols, csc.cols * self.K) if ntheta0 is None else ntheta0
@@ -228,7 +229,9 @@ class LatentDirichletAllocation:
         rc = _lib.lib().lda_b200_fit_begin(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data),
                                            _ptr(nphi0), _ptr(ntheta0), self.Rnd.src._s, ctr)
         _lib.check(rc, h)
+        self.w, self.d = csc.rows, csc.cols
         self._take(ctr)
+        self._has_model = True
         self.PerplexityTrace = []
         self.IterationsRun = 0
 
@@ -253,6 +256,41 @@ class LatentDirichletAllocation:
         theta = np.zeros((self.K, self.d), dtype=np.float64) if want_theta else None
         _lib.check(_lib.lib().lda_b200_fit_end(h, _ptr(theta)), h)
         return theta
+
+    def PartialFit(self, m, iterations=1, ntheta0=None, want_theta=False):
+        """OnlineTransformer.PartialFit (vectorisers.go:36-39; TODO at lda.go:147): `iterations` SCVB0 iterations over the
+        documents of m, continuing from the current model (a fresh random model on first use).  Returns self, or
+        the K x D doc-topic matrix of these documents when want_theta is set."""
+        csc = as_csc(m)
+        h = self._handle()
+        if ntheta0 is None and not self.DeviceInit:
+            if self.IterationsRun == 0 and not self._has_model:
+                raise ValueError("nlp: DeviceInit=False PartialFit needs an existing model")
+            ntheta0 = self._draws(csc.cols, csc.cols * self.K)
+        ntheta0 = None if ntheta0 is None else np.ascontiguousarray(ntheta0, dtype=np.float64)
+        theta = np.zeros((self.K, csc.cols), dtype=np.float64) if want_theta else None
+        ctr = self._counters()
+        rc = _lib.lib().lda_b200_partial_fit(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data),
+                                             _ptr(ntheta0), self.Rnd.src._s, ctr, iterations, _ptr(theta))
+        _lib.check(rc, h)
+        self.w, self.d = csc.rows, csc.cols
+        self._take(ctr)
+        self._has_model = True
+        return theta if want_theta else self
+
+    # ---- persistence in the library's binary style (weightings.go:97-116, dimreduction.go:111-153) ---------------
+    def Save(self, w):
+        """uint64 K, float64 rhoPhiT / rhoThetaT / wordsInCorpus (little endian), then nPhi (W x K) and nZ (1 x K) as
+        gonum `mat.Dense.MarshalBinaryTo` records"""
+        nphi, nz = self.GetState()
+        w.write(serialise_model(self.K, (self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus), nphi, nz))
+
+    def Load(self, r):
+        k, ctr, nphi, nz = deserialise_model(r.read())
+        self.K = k
+        self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus = ctr
+        self.SetState(nphi, nz)
+        self._has_model = True
 
     def Transform(self, m, theta0=None, return_passes=False):
         """lda.go:446-453: K x D doc-topic matrix for new documents under the fitted model"""
@@ -281,9 +319,15 @@ class LatentDirichletAllocation:
         _lib.check(rc, h)
         return out.value
 
+    def _dims(self):
+        w, k = C.c_int64(0), C.c_int32(0)
+        _lib.check(_lib.lib().lda_b200_get_dims(self._handle(), C.byref(w), C.byref(k)), self._h)
+        return int(w.value), int(k.value)
+
     def Components(self):
         """lda.go:414-416: K x W topic-word matrix"""
         h = self._handle()
+        self.w = self._dims()[0]
         out = np.zeros((self.K, self.w), dtype=np.float64)
         _lib.check(_lib.lib().lda_b200_components(h, _ptr(out)), h)
         return out
@@ -291,6 +335,7 @@ class LatentDirichletAllocation:
     # ---- persistence (TODO in the reference, lda.go:158) ------------------------------------------------------
     def GetState(self):
         h = self._handle()
+        self.w = self._dims()[0]
         nphi = np.zeros((self.w, self.K), dtype=np.float64)
         nz = np.zeros(self.K, dtype=np.float64)
         _lib.check(_lib.lib().lda_b200_get_state(h, _ptr(nphi), _ptr(nz)), h)
@@ -304,6 +349,44 @@ class LatentDirichletAllocation:
         h = self._handle()
         _lib.check(_lib.lib().lda_b200_set_state(h, nphi.shape[0], _ptr(nphi), _ptr(nz)), h)
         self.w = nphi.shape[0]
+
+
+_GONUM_VERSION = 0xFE000001  # gonum.org/v1/gonum/mat io.go storage header: version, 'G','F','A', unit, rows, cols, ku, kl
+
+
+def _dense_record(a):
+    import struct
+    a = np.ascontiguousarray(a, dtype="<f8")
+    return struct.pack("<IBBBBqqqq", _GONUM_VERSION, ord("G"), ord("F"), ord("A"), 0, a.shape[0], a.shape[1], 0, 0) + a.tobytes()
+
+
+def _read_dense(buf, off):
+    import struct
+    ver, form, packing, uplo, _unit, rows, cols, _ku, _kl = struct.unpack_from("<IBBBBqqqq", buf, off)
+    if ver != _GONUM_VERSION or (form, packing, uplo) != (ord("G"), ord("F"), ord("A")):
+        raise ValueError("nlp: not a gonum mat.Dense record")
+    off += 40
+    n = rows * cols
+    if rows < 0 or cols < 0 or off + 8 * n > len(buf):
+        raise ValueError("nlp: truncated mat.Dense record")
+    return np.frombuffer(buf, dtype="<f8", count=n, offset=off).reshape(rows, cols).copy(), off + 8 * n
+
+
+def serialise_model(k, counters, nphi, nz):
+    import struct
+    return struct.pack("<Qddd", k, *counters) + _dense_record(nphi) + _dense_record(np.asarray(nz).reshape(1, -1))
+
+
+def deserialise_model(buf):
+    import struct
+    if len(buf) < 32:
+        raise ValueError("nlp: unexpected EOF")  # io.ErrUnexpectedEOF in dimreduction.go:135
+    k, a, b, c = struct.unpack_from("<Qddd", buf, 0)
+    nphi, off = _read_dense(buf, 32)
+    nz, off = _read_dense(buf, off)
+    if nphi.shape[1] != k or nz.shape != (1, k):
+        raise ValueError("nlp: model dimensions do not match K")
+    return int(k), (a, b, c), nphi, nz[0]
 
 
 def NewLatentDirichletAllocation(k, device=None):

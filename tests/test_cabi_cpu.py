@@ -166,3 +166,19 @@ def test_product_does_not_import_the_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 for bad in ("import oracle", "from oracle", "liblda_oracle", "oracle/"):
                     assert bad not in text, (os.path.join(dirpath, f), bad)
+
+
+def test_model_serialisation_round_trip():
+    # Save/Load record layout (library style: dimreduction.go:111-153): uint64 K + gonum mat.Dense records
+    from nlp_b200.lda import deserialise_model, serialise_model
+    rng = np.random.default_rng(0)
+    nphi, nz = rng.random((37, 5)), rng.random(5)
+    buf = serialise_model(5, (3.0, 7.0, 1234.0), nphi, nz)
+    assert len(buf) == 32 + (40 + 37 * 5 * 8) + (40 + 5 * 8)
+    assert buf[:8] == (5).to_bytes(8, "little") and buf[32:36] == (0xFE000001).to_bytes(4, "little") and buf[36:39] == b"GFA"
+    k, ctr, a, b = deserialise_model(buf)
+    assert k == 5 and ctr == (3.0, 7.0, 1234.0) and np.array_equal(a, nphi) and np.array_equal(b, nz)
+    with pytest.raises(ValueError):
+        deserialise_model(buf[:100])
+    with pytest.raises(ValueError):
+        deserialise_model(b"\x00" * 200)

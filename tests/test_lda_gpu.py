@@ -254,6 +254,38 @@ def test_refit_quirks():
     assert lda.Rnd.src.state == o.rnd_state
 
 
+def test_partial_fit_and_persistence(tmp_path):
+    m = synth(240, 500, 30, block=60)
+    # one PartialFit on a fresh model == Fit with Iterations = 1 (init draws, rhoPhiT from 1, same minibatches)
+    o = new_oracle(7, Iterations=1, BatchSize=60, PerplexityEvaluationFrequency=0)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(7, BatchSize=60)
+    got = lda.PartialFit(m, want_theta=True)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    assert (lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus) == (o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus)
+    assert lda.Rnd.src.state == o.rnd_state
+    np.testing.assert_allclose(lda.GetState()[1], o.get_state()[1], rtol=1e-3)
+    # streaming: further PartialFit calls on new documents keep improving held-out perplexity
+    held = synth(60, 500, 30, block=60, seed=4242)
+    p0 = lda.Perplexity(held)
+    for s in range(6):
+        lda.PartialFit(synth(240, 500, 30, block=60, seed=100 + s))
+    assert lda.rhoPhiT == 1 + 4 * 7 and lda.Perplexity(held) < p0
+    with pytest.raises(_lib.LdaB200Error, match="same number of rows"):
+        lda.PartialFit(synth(60, 400, 30, block=60))
+    # Save / Load: a new object reproduces Transform exactly (same model, same RNG position)
+    path = tmp_path / "lda.bin"
+    with open(path, "wb") as f:
+        lda.Save(f)
+    lda2 = new_lda(3)
+    with open(path, "rb") as f:
+        lda2.Load(f)
+    assert (lda2.K, lda2.w, lda2.rhoPhiT, lda2.rhoThetaT, lda2.wordsInCorpus) == (7, 500, lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus)
+    lda2.Rnd.src.state = lda.Rnd.src.state
+    assert np.array_equal(lda.Transform(held), lda2.Transform(held))
+    assert np.array_equal(lda.Components(), lda2.Components())
+
+
 # ---- bit-exact pieces -------------------------------------------------------------------------------------------
 def test_ingest_roundtrip_bit_exact():
     import ctypes as C
