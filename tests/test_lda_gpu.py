@@ -151,6 +151,41 @@ def test_processes_concurrent_minibatches(k, procs, b, D):
     np.testing.assert_allclose(lda.GetState()[1], o.get_state()[1], rtol=1e-3)
 
 
+def test_committed_golden_vectors():
+    """the CUDA path against tests/golden/lda_golden.json (oracle-derived, see tests/golden/make_golden.py)"""
+    from tests.test_oracle_golden import _golden, _golden_input
+    g = _golden()
+    for case in g["cases"]:
+        f = dict(case["fields"])
+        sync = f.pop("SyncGroup", 1)
+        lda = new_lda(case["K"], Processes=sync, **f)
+        m = _golden_input(g, case["name"])
+        theta = lda.FitTransform(CSC(*m) if isinstance(m, tuple) else m)
+        assert lda.IterationsRun == case["iterations_run"], case["name"]
+        np.testing.assert_allclose(lda.PerplexityTrace, case["perplexity_trace"], rtol=PERP_RTOL)
+        assert np.abs(theta[:, :4] - np.array(case["theta_first_docs"])).max() <= THETA_ATOL
+        np.testing.assert_allclose(lda.GetState()[1], case["nz"], rtol=1e-3)
+        assert [lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus] == case["counters"]
+        assert list(lda.Rnd.src.state) == case["rnd_state"]
+
+
+def test_config1_full_fit_parity():
+    """configs[0] run to completion: 100 iterations of K=10 on 1k docs x 5k vocab, BatchSize 100, Processes 1, seed 0;
+    perplexity checked every 10 iterations.  fp32 device state must not drift from the float64 oracle."""
+    m = synth(1000, 5000, 100)
+    f = dict(PerplexityEvaluationFrequency=10, PerplexityTolerance=0.0, Iterations=100)
+    o = new_oracle(10, **f)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(10, **f)
+    got = lda.FitTransform(m)
+    rel = np.abs(np.array(lda.PerplexityTrace) / o.perplexity_trace - 1)
+    print("config1 full fit: perplexity", np.round(o.perplexity_trace, 3).tolist(), "max rel delta %.3g" % rel.max(),
+          "theta max abs delta %.3g" % np.abs(got - want).max())
+    assert rel.max() <= PERP_RTOL
+    assert np.abs(got - want).max() <= 5e-3
+    assert np.mean(got.argmax(0) == want.argmax(0)) >= 0.99
+
+
 def test_burn_in_passes_and_real_values():
     m = synth(120, 300, 30)
     rng = np.random.default_rng(1)

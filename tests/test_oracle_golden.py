@@ -110,3 +110,38 @@ def test_processes_gt_one_runs():
     theta = lda.FitTransform(FIXTURE_A)
     assert np.abs(1 - theta.sum(axis=0)).max() <= 1e-8
     assert lda.tokenVisits == 2 * 27 * 30
+
+
+def _golden():
+    import json
+    import os
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "lda_golden.json")))
+
+
+def _golden_input(g, name):
+    import corpus_synth
+    if name.startswith("fixture_A"):
+        return FIXTURE_A
+    if name.startswith("fixture_B"):
+        return FIXTURE_B
+    s = g["synthetic"]
+    indptr, ind, data = corpus_synth.generate(s["D"], s["W"], block=s["block"], mean_distinct=s["mean_distinct"],
+                                              n_topics=s["n_topics"])
+    assert (int(indptr[-1]), int(ind.sum()), float(data.sum())) == (s["nnz"], s["ind_checksum"], s["data_checksum"])
+    return (s["W"], s["D"], indptr, ind, data)
+
+
+def test_committed_golden_vectors_reproduce():
+    # tests/golden/lda_golden.json (tests/golden/make_golden.py): the oracle and the corpus generator are stable
+    g = _golden()
+    for case in g["cases"]:
+        o = O.LatentDirichletAllocation(case["K"], seed=0)
+        for k, v in case["fields"].items():
+            setattr(o, k, v)
+        theta = o.FitTransform(_golden_input(g, case["name"]))
+        assert o.iterationsRun == case["iterations_run"], case["name"]
+        np.testing.assert_allclose(o.perplexity_trace, case["perplexity_trace"], rtol=1e-9)
+        np.testing.assert_allclose(o.get_state()[1], case["nz"], rtol=1e-9)
+        np.testing.assert_allclose(theta[:, :4], case["theta_first_docs"], rtol=1e-7, atol=1e-12)
+        assert [o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus] == case["counters"]
+        assert list(o.rnd_state) == case["rnd_state"]
