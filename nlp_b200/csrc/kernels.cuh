@@ -4,6 +4,8 @@
 //   nPhi, nPhiHat  [W][Kp]   word-major, topic fastest (same as lda.go's [w*K+k]); Kp = K rounded up to 4
 //   nTheta         [Dl][Kp]  document-major, topic fastest (lda.go's [j*K+k]); Dl = documents owned by this GPU
 //   invZ           [Kp]      1/(nZ[k] + eta*W), 0 for the pad topics k >= K (this is what masks the pad)
+//   C              [W][Kp]   c[w,k] = (nPhi[w,k] + eta) * invZ[k]: the word-dependent factor of Eqn 5, rewritten by the
+//                            M-step kernels whenever nPhi / nZ change so that the per-token loop does not recompute it
 //   CSC            doc_ptr int64[Dl+1], ind int32[nnz], val fp32[nnz]   (token order preserved)
 //
 // Mapping: one document per "group" of LANES lanes (LANES = 32 for K > 64), each lane owning NV
@@ -47,9 +49,8 @@ struct DocsArgs {
     const float *val;
     const float *wc;         // [Dl]  lda.go:476-480
     float *theta;            // [Dl][Kp]
-    const float *nphi;       // [W][Kp]
+    const float *cmat;       // [W][Kp]  (nPhi + eta) * invZ
     float *nphi_hat;         // [W][Kp]   (main pass only)
-    const float *inv_z;      // [Kp]
     const float *log1m_rho;  // [passes+1]: ln(1 - RhoTheta.Calc(rhoThetaT + c)), c = 0..passes
     int32_t *passes_out;     // optional [Dl]
     int *doc_counter;        // dynamic document scheduler (reset by the blend kernel / host)
@@ -75,7 +76,7 @@ constexpr int MAX_CONCURRENT_MB = 16;
 // which keeps full relative accuracy when rho is small (the reference calls math.Pow 2K times per token).
 template <int LANES, int NV, int P, bool MAIN>
 __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int len, int maxlen, float l1m, float wcj,
-                                           float hat_scale, int g, float4 (&th)[NV], const float4 (&iz)[NV], const bool (&ok)[NV]) {
+                                           float hat_scale, int g, float4 (&th)[NV], const bool (&ok)[NV]) {
     for (int tile = 0; tile < maxlen; tile += LANES) {
         const int my = tile + g;
         const bool has = my < len;
@@ -89,7 +90,7 @@ __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int 
             const int w = __shfl_sync(FULL, wi, s, LANES);
 #pragma unroll
             for (int v = 0; v < NV; ++v)
-                if (s < ntile && w >= 0 && ok[v]) buf[s][v] = ldg4(a.nphi + (int64_t)w * a.Kp + 4 * (v * LANES + g));
+                if (s < ntile && w >= 0 && ok[v]) buf[s][v] = ldg4(a.cmat + (int64_t)w * a.Kp + 4 * (v * LANES + g));
         }
         for (int t0 = 0; t0 < ntile; t0 += P) {
 #pragma unroll
@@ -107,17 +108,17 @@ __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int 
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
                         if (tn < ntile && wn >= 0 && ok[v])
-                            buf[s][v] = ldg4(a.nphi + (int64_t)wn * a.Kp + 4 * (v * LANES + g));
+                            buf[s][v] = ldg4(a.cmat + (int64_t)wn * a.Kp + 4 * (v * LANES + g));
 
                     float4 gm[NV];
                     float part = 0.f;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
                         if (w >= 0 && ok[v]) {
-                            gm[v].x = (row[v].x + a.eta) * iz[v].x * (th[v].x + a.alpha);
-                            gm[v].y = (row[v].y + a.eta) * iz[v].y * (th[v].y + a.alpha);
-                            gm[v].z = (row[v].z + a.eta) * iz[v].z * (th[v].z + a.alpha);
-                            gm[v].w = (row[v].w + a.eta) * iz[v].w * (th[v].w + a.alpha);
+                            gm[v].x = row[v].x * (th[v].x + a.alpha);
+                            gm[v].y = row[v].y * (th[v].y + a.alpha);
+                            gm[v].z = row[v].z * (th[v].z + a.alpha);
+                            gm[v].w = row[v].w * (th[v].w + a.alpha);
                         } else {
                             gm[v] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
@@ -161,12 +162,8 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
     const int grp = lane / LANES;
 
     bool ok[NV];
-    float4 iz[NV];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        ok[v] = 4 * (v * LANES + g) < a.Kp;
-        iz[v] = ok[v] ? ldg4(a.inv_z + 4 * (v * LANES + g)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+    for (int v = 0; v < NV; ++v) ok[v] = 4 * (v * LANES + g) < a.Kp;
 
     for (;;) {
         int d0 = 0;
@@ -208,7 +205,7 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
                 prev = group_sum_d<LANES>(s);
             }
             const float l1m = a.log1m_rho[counter];  // lda.go:231
-            token_pass<LANES, NV, P, false>(a, base, done ? 0 : len, maxlen, l1m, wcj, 0.f, g, th, iz, ok);
+            token_pass<LANES, NV, P, false>(a, base, done ? 0 : len, maxlen, l1m, wcj, 0.f, g, th, ok);
             if (!done) executed = counter;
             if (chk && counter < a.passes) {  // lda.go:251-259
                 double s = 0.0;
@@ -221,7 +218,7 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
         if (FIT) {
             const float l1m = a.log1m_rho[a.passes];  // lda.go:274
             const float hs = valid ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
-            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, hs, g, th, iz, ok);
+            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, hs, g, th, ok);
         }
         if (valid) {
 #pragma unroll
@@ -235,11 +232,11 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
 // ---------------------------------------------------------------------------------------------------
 // Throughput kernel for K > 64 (one document per warp, LANES = 32).  Same arithmetic as above, restated so
 // that the per-token dependent chain and the instruction count are minimal:
-//   * registers hold tha_k = nTheta[j,k] + alpha.  With c_k = (nPhi[i,k]+eta) invZ_k (one FMA from the row),
+//   * registers hold tha_k = nTheta[j,k] + alpha.  With c_k = (nPhi[i,k]+eta) invZ_k (row i of the C matrix),
 //       S = sum_k c_k tha_k,  r = 1/S,  q = 1-(1-rho)^v:
 //       tha_k' = tha_k (1-q + q wc r c_k) + alpha q          == Eqn 9 applied to gamma_k = c_k tha_k r
 //       nPhiHat[i,k] += (N/b) r c_k tha_k                     (main pass)
-//   * the nPhi rows are staged through a per-warp shared-memory ring of R rows filled with cp.async
+//   * the rows of C are staged through a per-warp shared-memory ring of R rows filled with cp.async
 //     (LDGSTS, L2-only): the row of the token R positions ahead in the document's token stream -- which runs
 //     on across tile and pass boundaries -- is always in flight.  Each lane copies, and later reads, only its
 //     own 16-byte slices of a row, so the ring needs no barrier: the per-thread cp.async group order is enough.
@@ -274,7 +271,6 @@ constexpr int docs32_smem_bytes(int NV) { return 8 * docs32_ring_rows(NV) * NV *
 template <int NV, bool FULLK, bool FIT>
 __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
     constexpr int R = docs32_ring_rows(NV);
-    constexpr bool EZ = NV <= 2;  // keep eta*invZ in registers only where the register budget allows
     extern __shared__ float4 ring_all[];
     const int lane = threadIdx.x & 31;
     float4 *ring = ring_all + (threadIdx.x >> 5) * (R * NV * 32) + lane;  // slot s, slice v: ring[(s*NV+v)*32]
@@ -282,8 +278,8 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     const unsigned row_bytes = 4u * (unsigned)Kp;   // W*Kp*4 < 2^32 is checked by the host
     unsigned lane_bytes = 16u * (unsigned)lane;
     asm volatile("" : "+r"(lane_bytes));  // keep it in a register: ptxas otherwise re-derives it from %tid per token
-    const float alpha = a.alpha, eta = a.eta;
-    const char *__restrict__ nphi_b = reinterpret_cast<const char *>(a.nphi);
+    const float alpha = a.alpha;
+    const char *__restrict__ cmat_b = reinterpret_cast<const char *>(a.cmat);
     const int32_t *__restrict__ ind = a.ind;
     const float *__restrict__ val = a.val;
     const float *__restrict__ tab = a.log1m_rho;
@@ -291,17 +287,12 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     const int total_passes = passes + (FIT ? 1 : 0);
 
     bool ok[NV];
-    float4 iz[NV], ez[EZ ? NV : 1];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-        ok[v] = FULLK || 4 * (v * 32 + lane) < Kp;
-        iz[v] = ok[v] ? ldg4(a.inv_z + 4 * (v * 32 + lane)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (EZ) ez[v] = make_float4(eta * iz[v].x, eta * iz[v].y, eta * iz[v].z, eta * iz[v].w);
-    }
+    for (int v = 0; v < NV; ++v) ok[v] = FULLK || 4 * (v * 32 + lane) < Kp;
     // asynchronous copy of this lane's slices of row w into ring slot `slot`; always closes one cp.async group
     auto issue = [&](int slot, int w) {
         if (w >= 0) {
-            const char *src = nphi_b + ((unsigned)w * row_bytes + lane_bytes);
+            const char *src = cmat_b + ((unsigned)w * row_bytes + lane_bytes);
 #pragma unroll
             for (int v = 0; v < NV; ++v)
                 if (ok[v]) cp_async16(ring + (slot * NV + v) * 32, reinterpret_cast<const float *>(src + 512 * v));
@@ -395,20 +386,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                 cp_async_wait<R - 1>();  // the oldest outstanding group (this token's row) has landed
                 float4 c[NV];
 #pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    const float4 row = ok[v] ? ring[(slot * NV + v) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (EZ) {
-                        c[v].x = fmaf(row.x, iz[v].x, ez[v].x);
-                        c[v].y = fmaf(row.y, iz[v].y, ez[v].y);
-                        c[v].z = fmaf(row.z, iz[v].z, ez[v].z);
-                        c[v].w = fmaf(row.w, iz[v].w, ez[v].w);
-                    } else {
-                        c[v].x = (row.x + eta) * iz[v].x;
-                        c[v].y = (row.y + eta) * iz[v].y;
-                        c[v].z = (row.z + eta) * iz[v].z;
-                        c[v].w = (row.w + eta) * iz[v].w;
-                    }
-                }
+                for (int v = 0; v < NV; ++v) c[v] = ok[v] ? ring[(slot * NV + v) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
                 issue(slot, wn);  // refill the slot just consumed with the row R positions ahead
                 slot = slot + 1 == R ? 0 : slot + 1;
 
@@ -484,43 +462,20 @@ __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, 
     if (c < n) out[c] = (float)log1p(-S / pow(Tau + t0 + (double)c, Kappa));
 }
 
-// M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58):
-//   nPhi = A*nPhi + C*nPhiHat ; nPhiHat = 0 ; nZHat = colsum(nPhiHat) (== the reference's running sum, lda.go:295)
-// and, in the last block to finish: nZ = A*nZ + C*nZHat ; invZ = 1/(nZ + eta*W) ; scheduler reset.
+// M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58), as three launches on the stream:
+//   hat_colsum_kernel : nZHat[k] = sum_w nPhiHat[w,k]   (== the reference's running sum, lda.go:295)
+//   nz_update_kernel  : nZ = A nZ + C nZHat ; invZ = 1/(nZ + eta W) ; scheduler reset              (lda.go:313-317)
+//   phi_blend_kernel  : nPhi = A nPhi + C nPhiHat ; nPhiHat = 0 ; c = (nPhi + eta) invZ            (lda.go:303-310)
 // blockDim.x = VPR*RPB with VPR = Kp/4 float4 per row, so a thread always owns the same 4 topics.
-struct BlendArgs {
-    float *nphi;
-    float *nphi_hat;
-    double *nz;      // [Kp]
-    double *nzhat;   // [Kp] scratch, zero on entry, zero on exit
-    float *inv_z;    // [Kp]
-    unsigned *ticket;
-    int *doc_counter;
-    int64_t W;
-    int K, Kp;
-    float A, C;
-    double Ad, Cd;
-    double etaW;
-};
-
-__global__ void __launch_bounds__(256) phi_blend_kernel(const BlendArgs a) {
+__global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64_t W, int Kp, double *nzhat) {
     extern __shared__ float4 sm4[];
-    const int VPR = a.Kp >> 2;
+    const int VPR = Kp >> 2;
     const int RPB = blockDim.x / VPR;
     const int col = threadIdx.x % VPR;
     const int rslot = threadIdx.x / VPR;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < a.W; r += (int64_t)gridDim.x * RPB) {
-        float4 *pp = reinterpret_cast<float4 *>(a.nphi + r * a.Kp) + col;
-        float4 *hp = reinterpret_cast<float4 *>(a.nphi_hat + r * a.Kp) + col;
-        float4 p = *pp;
-        const float4 h = *hp;
-        p.x = fmaf(a.A, p.x, a.C * h.x);
-        p.y = fmaf(a.A, p.y, a.C * h.y);
-        p.z = fmaf(a.A, p.z, a.C * h.z);
-        p.w = fmaf(a.A, p.w, a.C * h.w);
-        *pp = p;
-        *hp = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < W; r += (int64_t)gridDim.x * RPB) {
+        const float4 h = reinterpret_cast<const float4 *>(hat + r * Kp)[col];
         acc.x += h.x;
         acc.y += h.y;
         acc.z += h.z;
@@ -537,32 +492,60 @@ __global__ void __launch_bounds__(256) phi_blend_kernel(const BlendArgs a) {
             sz += t.z;
             sw += t.w;
         }
-        atomicAdd(a.nzhat + 4 * col + 0, sx);
-        atomicAdd(a.nzhat + 4 * col + 1, sy);
-        atomicAdd(a.nzhat + 4 * col + 2, sz);
-        atomicAdd(a.nzhat + 4 * col + 3, sw);
+        atomicAdd(nzhat + 4 * col + 0, sx);
+        atomicAdd(nzhat + 4 * col + 1, sy);
+        atomicAdd(nzhat + 4 * col + 2, sz);
+        atomicAdd(nzhat + 4 * col + 3, sw);
     }
-    __shared__ bool last;
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1);
-    __syncthreads();
-    if (last) {
-        __threadfence();
-        for (int k = threadIdx.x; k < a.Kp; k += blockDim.x) {
-            if (k < a.K) {
-                const double z = a.Ad * a.nz[k] + a.Cd * __ldcg(a.nzhat + k);
-                a.nz[k] = z;
-                a.inv_z[k] = (float)(1.0 / (z + a.etaW));
-            } else {
-                a.inv_z[k] = 0.f;
-            }
-            a.nzhat[k] = 0.0;
+}
+
+__global__ void nz_update_kernel(double *nz, double *nzhat, float *inv_z, int *doc_counter, int K, int Kp, double Ad,
+                                 double Cd, double etaW) {
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        if (k < K) {
+            const double z = Ad * nz[k] + Cd * nzhat[k];
+            nz[k] = z;
+            inv_z[k] = (float)(1.0 / (z + etaW));
+        } else {
+            inv_z[k] = 0.f;
         }
-        if (threadIdx.x == 0) {
-            *a.ticket = 0u;
-            *a.doc_counter = 0;
+        nzhat[k] = 0.0;
+    }
+    if (threadIdx.x == 0) *doc_counter = 0;
+}
+
+struct BlendArgs {
+    float *nphi;
+    float *nphi_hat;  // may be nullptr: only c is refreshed from nPhi and invZ
+    float *cmat;
+    const float *inv_z;
+    int64_t W;
+    int Kp;
+    float A, C, eta;
+};
+
+__global__ void __launch_bounds__(256) phi_blend_kernel(const BlendArgs a) {
+    const int VPR = a.Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    const float4 iz = reinterpret_cast<const float4 *>(a.inv_z)[col];
+    const float4 ez = make_float4(a.eta * iz.x, a.eta * iz.y, a.eta * iz.z, a.eta * iz.w);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < a.W; r += (int64_t)gridDim.x * RPB) {
+        float4 *pp = reinterpret_cast<float4 *>(a.nphi + r * a.Kp) + col;
+        float4 p = *pp;
+        if (a.nphi_hat) {
+            float4 *hp = reinterpret_cast<float4 *>(a.nphi_hat + r * a.Kp) + col;
+            const float4 h = *hp;
+            p.x = fmaf(a.A, p.x, a.C * h.x);
+            p.y = fmaf(a.A, p.y, a.C * h.y);
+            p.z = fmaf(a.A, p.z, a.C * h.z);
+            p.w = fmaf(a.A, p.w, a.C * h.w);
+            *pp = p;
+            *hp = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        reinterpret_cast<float4 *>(a.cmat + r * a.Kp)[col] =
+            make_float4(fmaf(p.x, iz.x, ez.x), fmaf(p.y, iz.y, ez.y), fmaf(p.z, iz.z, ez.z), fmaf(p.w, iz.w, ez.w));
     }
 }
 
@@ -676,7 +659,6 @@ struct BarrierArgs {
     double *nz;
     float *inv_z;
     double Ad, Cd, etaW;
-    unsigned *ticket;
     int *doc_counter;
     int *err;
 };
@@ -717,10 +699,7 @@ __global__ void __launch_bounds__(256) xgpu_barrier_kernel(const BarrierArgs a) 
                 a.inv_z[k] = 0.f;
             }
         }
-        if (threadIdx.x == 0) {
-            *a.ticket = 0u;
-            *a.doc_counter = 0;
-        }
+        if (threadIdx.x == 0) *a.doc_counter = 0;
     }
 }
 

@@ -70,6 +70,7 @@ struct lda_b200_handle {
     float *nphi = nullptr;
     double *nz = nullptr;
     float *inv_z = nullptr;
+    float *cmat = nullptr;  // (nPhi + eta) * invZ, [W][Kp], kept current by the M-step kernels
 
     // scratch
     float *nphi_hat = nullptr;
@@ -350,6 +351,7 @@ int ensure_model(lda_b200_handle *h, int64_t W) {
     h->fitted = false;
     TRY(dalloc(h, &h->nphi, (size_t)W * Kp));
     TRY(dalloc(h, &h->nphi_hat, (size_t)W * Kp));
+    TRY(dalloc(h, &h->cmat, (size_t)W * Kp));
     TRY(dalloc(h, &h->nz, (size_t)Kp));
     TRY(dalloc(h, &h->nzhat, (size_t)Kp));
     TRY(dalloc(h, &h->colsum, (size_t)Kp));
@@ -525,8 +527,21 @@ int refresh_nz_from_nphi(lda_b200_handle *h) {
     KCHECK();
     return 0;
 }
+// invZ from nZ and c = (nPhi + eta) invZ from nPhi (after init / set_state / a change of Eta)
 int refresh_inv_z(lda_b200_handle *h) {
     inv_z_kernel<<<(h->Kp + 127) / 128, 128, 0, h->stream>>>(h->nz, h->inv_z, h->K, h->Kp, h->cfg.eta * (double)h->W);
+    KCHECK();
+    BlendArgs ba;
+    ba.nphi = h->nphi;
+    ba.nphi_hat = nullptr;
+    ba.cmat = h->cmat;
+    ba.inv_z = h->inv_z;
+    ba.W = h->W;
+    ba.Kp = h->Kp;
+    ba.A = 1.f;
+    ba.C = 0.f;
+    ba.eta = (float)h->cfg.eta;
+    phi_blend_kernel<<<h->sms * 4, blend_block(h->Kp), 0, h->stream>>>(ba);
     KCHECK();
     return 0;
 }
@@ -735,9 +750,8 @@ DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
     a.val = c.val;
     a.wc = c.wc;
     a.theta = c.theta;
-    a.nphi = h->nphi;
+    a.cmat = h->cmat;
     a.nphi_hat = h->nphi_hat;
-    a.inv_z = h->inv_z;
     a.log1m_rho = h->rho_tab;
     a.passes_out = nullptr;
     a.doc_counter = h->doc_counter;
@@ -858,6 +872,7 @@ void lda_b200_destroy(lda_b200_handle *h) {
     free_corpus(h, h->fitc);
     dfree(h, &h->nphi);
     dfree(h, &h->nphi_hat);
+    dfree(h, &h->cmat);
     dfree(h, &h->nz);
     dfree(h, &h->nzhat);
     dfree(h, &h->colsum);
@@ -883,7 +898,12 @@ int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg) {
     if (!h) return LDA_B200_EINVAL;
     TRY(validate_config(h, cfg));
     if (h->fit_open && cfg->K != h->cfg.K) return fail(h, LDA_B200_EINVAL, "K cannot change during a fit");
+    const bool eta_changed = cfg->eta != h->cfg.eta;
     h->cfg = *cfg;
+    if (eta_changed && h->fitted && !h->fit_open && h->K == cfg->K) {
+        CU(cudaSetDevice(h->device));
+        TRY(refresh_inv_z(h));  // invZ and c = (nPhi + eta) invZ depend on Eta
+    }
     return 0;
 }
 
@@ -1092,7 +1112,6 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 bar.Ad = Ad;
                 bar.Cd = Cd;
                 bar.etaW = cfg.eta * (double)h->W;
-                bar.ticket = h->ticket;
                 bar.doc_counter = h->doc_counter;
                 bar.err = h->err_flag;
                 int slot;
@@ -1118,6 +1137,18 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 bar.epoch = ++h->epoch;
                 xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
                 KCHECK();
+                BlendArgs ca;  // c = (nPhi' + eta) invZ' over the local replica
+                ca.nphi = h->nphi;
+                ca.nphi_hat = nullptr;
+                ca.cmat = h->cmat;
+                ca.inv_z = h->inv_z;
+                ca.W = h->W;
+                ca.Kp = h->Kp;
+                ca.A = 1.f;
+                ca.C = 0.f;
+                ca.eta = (float)cfg.eta;
+                phi_blend_kernel<<<h->sms * 4, bs, 0, h->stream>>>(ca);
+                KCHECK();
                 TRY(ev_end(h, slot));
                 h->hat_cur ^= 1;
                 h->nphi_hat = h->hat_buf[h->hat_cur];
@@ -1128,26 +1159,25 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                     NC(nccl().AllReduce(h->nphi_hat, h->nphi_hat, (size_t)h->W * h->Kp, ncclFloat, ncclSum, h->comm, h->stream));
                     TRY(ev_end(h, slot));
                 }
-                BlendArgs ba;
-                ba.nphi = h->nphi;
-                ba.nphi_hat = h->nphi_hat;
-                ba.nz = h->nz;
-                ba.nzhat = h->nzhat;
-                ba.inv_z = h->inv_z;
-                ba.ticket = h->ticket;
-                ba.doc_counter = h->doc_counter;
-                ba.W = h->W;
-                ba.K = h->K;
-                ba.Kp = h->Kp;
-                ba.Ad = Ad;
-                ba.Cd = Cd;
-                ba.A = (float)ba.Ad;
-                ba.C = (float)ba.Cd;
-                ba.etaW = cfg.eta * (double)h->W;
                 const int bs = blend_block(h->Kp);
                 int slot;
                 TRY(ev_begin(h, 1, &slot));
-                phi_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(ba);
+                hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->nzhat);
+                KCHECK();
+                nz_update_kernel<<<1, 256, 0, h->stream>>>(h->nz, h->nzhat, h->inv_z, h->doc_counter, h->K, h->Kp, Ad, Cd,
+                                                           cfg.eta * (double)h->W);
+                KCHECK();
+                BlendArgs ba;
+                ba.nphi = h->nphi;
+                ba.nphi_hat = h->nphi_hat;
+                ba.cmat = h->cmat;
+                ba.inv_z = h->inv_z;
+                ba.W = h->W;
+                ba.Kp = h->Kp;
+                ba.A = (float)Ad;
+                ba.C = (float)Cd;
+                ba.eta = (float)cfg.eta;
+                phi_blend_kernel<<<h->sms * 4, bs, 0, h->stream>>>(ba);
                 KCHECK();
                 TRY(ev_end(h, slot));
             }
