@@ -174,6 +174,12 @@ int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const in
                               const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
                               double *wc_out, double *n_out);
 
+/* sparse.ToCSC() (lda.go:464-466) of a CSR term x document matrix, on the device: row_ptr[W+1], col_ind[nnz]
+ * (document ids), data[nnz] -> indptr_out[D+1], ind_out[nnz] (word ids, ascending inside a document), data_out[nnz].
+ * The result is what lda_b200_fit / transform / perplexity take; fewer than 2^31 entries. */
+int lda_b200_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *row_ptr, const int64_t *col_ind,
+                        const double *data, int64_t *indptr_out, int64_t *ind_out, double *data_out);
+
 /* Resident-corpus API used by bench.py to time the fit loop with the inputs already in
  * HBM (the `value` leg); lda_b200_fit is these three calls back to back. */
 int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,

@@ -57,6 +57,7 @@ SYMBOLS = {
     "lda_b200_pcg_fill": (None, [C.POINTER(Pcg), C.c_int64, C.c_int64, _P]),
     "lda_b200_pcg_advance": (None, [C.POINTER(Pcg), C.c_uint64]),
     "lda_b200_ingest_roundtrip": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    "lda_b200_csr_to_csc": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "lda_b200_fit_begin": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters)]),
     "lda_b200_fit_iterate": (C.c_int, [_P, C.c_int32, C.POINTER(Counters), _P, C.c_int32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),

@@ -921,6 +921,41 @@ __global__ void unpad_rows_kernel(const float *src, double *dst, int64_t R, int 
     }
 }
 
+// ---- CSR -> CSC (sparse.ToCSC(), lda.go:464-466) on the device -----------------------------------------------
+// row id of every stored entry of a CSR matrix (one warp per row)
+__global__ void __launch_bounds__(256) csr_expand_rows_kernel(const int64_t *row_ptr, int64_t W, int32_t *rows) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp; r < W; r += nwarps)
+        for (int64_t p = row_ptr[r] + lane; p < row_ptr[r + 1]; p += 32) rows[p] = (int32_t)r;
+}
+__global__ void iota_kernel(uint32_t *out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) out[i] = (uint32_t)i;
+}
+// indptr[j] = first position of column j in the column-sorted entry list (lower bound), indptr[D] = nnz
+__global__ void csc_indptr_kernel(const int32_t *sorted_cols, int64_t nnz, int64_t D, int64_t *indptr) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= D; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = nnz;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if ((int64_t)sorted_cols[mid] < j)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        indptr[j] = lo;
+    }
+}
+__global__ void csc_gather_kernel(const uint32_t *perm, const int32_t *rows, const double *data, int64_t n, int64_t *ind_out,
+                                  double *data_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t p = perm[i];
+        ind_out[i] = (int64_t)rows[p];
+        data_out[i] = data[p];
+    }
+}
+
 // wc[j] = sum of the document's values (lda.go:476-480), float64 accumulation; *n_total += sum_j wc[j] (lda.go:481)
 __global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, const float *val, int n_docs, float *wc,
                                                      double *wc64, double *n_total) {

@@ -14,6 +14,8 @@
 #include <string>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/lda_b200.h"
 #include "kernels.cuh"
 #include "nccl_dl.h"
@@ -1425,6 +1427,90 @@ int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const in
     if (!rc) rc = back();
     free_corpus(h, c);
     if (wc64) cudaFreeAsync(wc64, h->stream);
+    return rc;
+}
+
+// sparse.ToCSC() of a CSR term x document matrix on the device.  The radix sort on the column
+// (document) id is stable, so inside a document the rows stay in ascending order -- exactly what the reference's
+// host-side conversion produces and what fixes the token order of the path.
+int lda_b200_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *row_ptr, const int64_t *col_ind,
+                        const double *data, int64_t *indptr_out, int64_t *ind_out, double *data_out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (W < 0 || D < 0 || !row_ptr || !indptr_out) return fail(h, LDA_B200_EINVAL, "bad CSR arguments");
+    const int64_t nnz = row_ptr[W] - row_ptr[0];
+    if (row_ptr[0] != 0) return fail(h, LDA_B200_EINVAL, "row_ptr[0] must be 0");
+    for (int64_t r = 0; r < W; ++r)
+        if (row_ptr[r + 1] < row_ptr[r]) return fail(h, LDA_B200_EINVAL, "row_ptr is not non-decreasing at row %lld", (long long)r);
+    if (nnz >= (1LL << 31) || D >= (1LL << 31) || W >= (1LL << 31))
+        return fail(h, LDA_B200_EUNSUPPORTED, "CSR with 2^31 or more entries / rows / columns");
+    if (nnz > 0 && (!col_ind || !data || !ind_out || !data_out)) return fail(h, LDA_B200_EINVAL, "NULL CSR array");
+    CU(cudaSetDevice(h->device));
+    int64_t *d_rowptr = nullptr, *d_indptr = nullptr, *d_ind64 = nullptr;
+    int32_t *d_cols = nullptr, *d_cols2 = nullptr, *d_rows = nullptr;
+    uint32_t *d_perm = nullptr, *d_perm2 = nullptr;
+    double *d_data = nullptr, *d_data2 = nullptr;
+    void *d_tmp = nullptr;
+    auto run = [&]() -> int {
+        TRY(dalloc(h, &d_rowptr, (size_t)W + 1));
+        TRY(dalloc(h, &d_indptr, (size_t)D + 1));
+        TRY(dalloc(h, &d_cols, (size_t)nnz));
+        TRY(dalloc(h, &d_cols2, (size_t)nnz));
+        TRY(dalloc(h, &d_rows, (size_t)nnz));
+        TRY(dalloc(h, &d_perm, (size_t)nnz));
+        TRY(dalloc(h, &d_perm2, (size_t)nnz));
+        TRY(dalloc(h, &d_data, (size_t)nnz));
+        TRY(dalloc(h, &d_data2, (size_t)nnz));
+        TRY(dalloc(h, &d_ind64, (size_t)nnz));
+        CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+        const int64_t chunk = (int64_t)(h->stage_bytes / 8);
+        for (int64_t p = 0; p < nnz; p += chunk) {
+            const int64_t n = std::min(chunk, nnz - p);
+            CU(cudaMemcpyAsync(h->stage, col_ind + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, d_cols + p, n, D, h->err_flag);
+            KCHECK();
+        }
+        CU(cudaMemcpyAsync(d_data, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        if (nnz > 0) {
+            csr_expand_rows_kernel<<<grid_for(W * 32, 256, h->sms * 8), 256, 0, h->stream>>>(d_rowptr, W, d_rows);
+            KCHECK();
+            iota_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm, nnz);
+            KCHECK();
+            int bits = 1;
+            while ((1LL << bits) < D) ++bits;
+            size_t tmp_bytes = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
+            CU(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, h->stream));
+            CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
+            h->launches += 4;
+            csc_gather_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm2, d_rows, d_data, nnz, d_ind64, d_data2);
+            KCHECK();
+        }
+        csc_indptr_kernel<<<grid_for(D + 1, 256, h->sms * 8), 256, 0, h->stream>>>(d_cols2, nnz, D, d_indptr);
+        KCHECK();
+        CU(cudaMemcpyAsync(indptr_out, d_indptr, ((size_t)D + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        if (nnz > 0) {
+            CU(cudaMemcpyAsync(ind_out, d_ind64, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(data_out, d_data2, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (bad) return fail(h, LDA_B200_EINVAL, "a column index lies outside [0, %lld)", (long long)D);
+        return 0;
+    };
+    const int rc = run();
+    dfree(h, &d_rowptr);
+    dfree(h, &d_indptr);
+    dfree(h, &d_cols);
+    dfree(h, &d_cols2);
+    dfree(h, &d_rows);
+    dfree(h, &d_perm);
+    dfree(h, &d_perm2);
+    dfree(h, &d_data);
+    dfree(h, &d_data2);
+    dfree(h, &d_ind64);
+    if (d_tmp) cudaFreeAsync(d_tmp, h->stream);
     return rc;
 }
 

@@ -150,6 +150,22 @@ class LatentDirichletAllocation:
             _lib.lib().lda_b200_comm_info(self._h, C.byref(r), C.byref(n), C.byref(p))
         return r.value, n.value, bool(p.value)
 
+    def ToCSC(self, m):
+        """sparse.ToCSC() (lda.go:464-466) of a scipy CSR term x document matrix on the GPU -> nlp_b200.CSC"""
+        csr = m.tocsr() if getattr(m, "format", None) != "csr" else m
+        csr.sort_indices()
+        rows, cols = csr.shape
+        rp = np.ascontiguousarray(csr.indptr, dtype=np.int64)
+        ci = np.ascontiguousarray(csr.indices, dtype=np.int64)
+        dv = np.ascontiguousarray(csr.data, dtype=np.float64)
+        indptr = np.zeros(cols + 1, dtype=np.int64)
+        ind = np.zeros(ci.size, dtype=np.int64)
+        data = np.zeros(ci.size, dtype=np.float64)
+        h = self._handle()
+        _lib.check(_lib.lib().lda_b200_csr_to_csc(h, rows, cols, _ptr(rp), _ptr(ci), _ptr(dv), _ptr(indptr), _ptr(ind),
+                                                  _ptr(data)), h)
+        return CSC(rows, cols, indptr, ind, data)
+
     def Close(self):
         if self._h is not None:
             _lib.lib().lda_b200_destroy(self._h)

@@ -343,6 +343,32 @@ def test_ingest_roundtrip_bit_exact():
     assert n.value == m.data.sum()                                     # lda.go:481
 
 
+def test_device_csr_to_csc_bit_exact():
+    # the reference converts with sparse.ToCSC() on the host (lda.go:464-466); the device transpose must give the
+    # identical CSC (rows ascending inside every document), including empty rows / documents
+    import scipy.sparse as sp
+    lda = new_lda(3)
+    rng = np.random.default_rng(3)
+    for (W, D, dens) in [(50, 70, 0.1), (1000, 300, 0.02), (7, 5000, 0.3), (300, 1, 0.5), (1, 40, 0.5), (64, 64, 0.0)]:
+        a = sp.random(W, D, density=dens, format="csr", random_state=rng, data_rvs=lambda n: rng.integers(1, 9, n).astype(float))
+        got = lda.ToCSC(a)
+        want = a.tocsc()
+        want.sort_indices()
+        assert (got.rows, got.cols) == (W, D)
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.ind, want.indices)
+        assert np.array_equal(got.data, want.data)
+    m = synth(400, 3000, 60)
+    import scipy.sparse as sp2
+    csc = sp2.csc_matrix((m.data, m.ind, m.indptr), shape=(m.rows, m.cols))
+    got = lda.ToCSC(csc.tocsr())
+    assert np.array_equal(got.indptr, m.indptr) and np.array_equal(got.ind, m.ind) and np.array_equal(got.data, m.data)
+    bad = csc.tocsr().copy()
+    bad.indices = bad.indices.astype(np.int64)
+    bad.indices[3] = 400
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.ToCSC(bad)
+
+
 def test_device_pcg_init_is_bit_exact():
     # Iterations = 0: the state read back is the initial draw of lda.go:199-205, produced on the GPU
     W, D, K = 37, 11, 7
