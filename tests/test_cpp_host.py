@@ -1,0 +1,37 @@
+"""The C++ host mirror (include/nlp_lda.hpp) and the reference's tests restated in C++ (tests/cpp/lda_test.cpp):
+compiled against liblda_b200.so on CPU, executed on the B200 box."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "lda_test")
+
+
+def build():
+    src = os.path.join(ROOT, "tests", "cpp", "lda_test.cpp")
+    libdir = os.path.join(ROOT, "nlp_b200")
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+           "-L", libdir, "-llda_b200", "-Wl,-rpath," + libdir]
+    subprocess.check_call(cmd)
+    return EXE
+
+
+def test_cpp_host_mirror_compiles_and_links():
+    assert os.path.exists(build())
+
+
+def test_cpp_host_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([build()], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_tests_in_cpp():
+    r = subprocess.run([build()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASS" in r.stdout
