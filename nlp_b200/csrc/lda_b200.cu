@@ -89,6 +89,13 @@ struct lda_b200_handle {
     size_t stage_bytes = 0;
     double *h_pinned = nullptr;  // small pinned read-back area
 
+    // streaming of the result during the last iteration of lda_b200_fit (second stream)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_ev = nullptr;
+    double *pending_theta_out = nullptr;  // caller's K x D buffer, set by lda_b200_fit for the duration of the call
+    double *dout = nullptr;               // K x Dl normalised, transposed result on the device
+    bool theta_streamed = false;
+
     // fit run
     Corpus fitc;
     bool fit_open = false;
@@ -745,6 +752,26 @@ int write_theta_out(lda_b200_handle *h, const Corpus &c, double *theta_out) {
     return 0;
 }
 
+// During the last iteration of a fit the nTheta rows of a launch are final as soon as that launch has finished:
+// normalise + transpose them (lda.go:541) right behind the launch and copy them to the caller's K x D matrix on the
+// copy stream, so the device->host transfer overlaps the remaining launches of the iteration.
+int stream_theta_range(lda_b200_handle *h, const Corpus &c, int64_t l0, int64_t l1) {
+    if (l1 <= l0) return 0;
+    transpose_out_kernel<true><<<(unsigned)((l1 - l0 + 31) / 32), 256, 0, h->stream>>>(c.theta + l0 * h->Kp, l1 - l0, h->K, h->Kp,
+                                                                                      nullptr, h->dout + l0, c.Dl);
+    KCHECK();
+    CU(cudaEventRecord(h->copy_ev, h->stream));
+    CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
+    for (const Segment &s : c.segs) {
+        const int64_t a = std::max(l0, s.l0), b = std::min(l1, s.l0 + (s.g1 - s.g0));
+        if (a >= b) continue;
+        CU(cudaMemcpy2DAsync(h->pending_theta_out + s.g0 + (a - s.l0), (size_t)c.D * sizeof(double), h->dout + a,
+                             (size_t)c.Dl * sizeof(double), (size_t)(b - a) * sizeof(double), (size_t)h->K,
+                             cudaMemcpyDeviceToHost, h->copy_stream));
+    }
+    return 0;
+}
+
 DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
     DocsArgs a;
     a.doc_ptr = c.doc_ptr;
@@ -840,6 +867,8 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         CU(cudaGetDeviceProperties(&prop, device));
         h->sms = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
         cudaMemPool_t pool;
         CU(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = UINT64_MAX;
@@ -892,6 +921,8 @@ void lda_b200_destroy(lda_b200_handle *h) {
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
     }
+    if (h->copy_ev) cudaEventDestroy(h->copy_ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1072,6 +1103,12 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
     for (int it = 0; it < n_iterations && !h->stopped && h->it_done < cfg.iterations; ++it) {
         ctr->rho_theta_t += 1;  // lda.go:502
         TRY(fill_rho_table(h, ctr->rho_theta_t, B + 1));
+        // last iteration of lda_b200_fit: stream the result out behind every launch
+        const bool stream_out = h->pending_theta_out && h->it_done + 1 == cfg.iterations && c.Dl > 0;
+        if (stream_out) {
+            TRY(dalloc(h, &h->dout, (size_t)h->K * c.Dl));
+            h->theta_streamed = true;
+        }
         for (int64_t s = 0; s < nsteps; ++s) {
             // minibatches s*G .. s*G+n_s-1 are all computed from the same nPhi snapshot and then blended one after
             // the other in index order (lda.go:299-317 n_s times):  nPhi' = A nPhi + sum_g c_g nPhiHat_g
@@ -1099,6 +1136,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 TRY(ev_begin(h, 0, &slot));
                 TRY(launch_docs<true>(h, a, c.order));
                 TRY(ev_end(h, slot));
+                if (stream_out) TRY(stream_theta_range(h, c, a.doc_begin, a.doc_end));
             }
             const double Ad = A, Cd = (n_s > 1) ? 1.0 : c_single;
             if (h->peer_ok) {
@@ -1226,7 +1264,16 @@ int lda_b200_fit_end(lda_b200_handle *h, double *theta_out) {
     if (!h->fit_open) return fail(h, LDA_B200_ESTATE, "lda_b200_fit_end without lda_b200_fit_begin");
     CU(cudaSetDevice(h->device));
     PhaseTimer pt(h->stream);
-    int rc = write_theta_out(h, h->fitc, theta_out);
+    int rc = 0;
+    if (h->theta_streamed && theta_out == h->pending_theta_out) {
+        cudaError_t e = cudaStreamSynchronize(h->copy_stream);
+        if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "theta read-back failed: %s", cudaGetErrorString(e));
+        pt.lap("theta_out: wait for streamed copy");
+    } else {
+        rc = write_theta_out(h, h->fitc, theta_out);
+    }
+    dfree(h, &h->dout);
+    h->theta_streamed = false;
     pt.t0 = PhaseTimer::now();
     free_corpus(h, h->fitc);
     pt.lap("fit_end: free corpus");
@@ -1242,14 +1289,21 @@ int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr
     PhaseTimer pt(h->stream);
     TRY(lda_b200_fit_begin(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr));
     pt.lap("fit: begin total");
+    h->pending_theta_out = theta_out;
+    h->theta_streamed = false;
     int rc = lda_b200_fit_iterate(h, h->cfg.iterations, ctr, perp_trace, perp_cap, n_evals, iters_run, nullptr, nullptr);
     pt.lap("fit: iterations");
     if (rc) {
+        cudaStreamSynchronize(h->copy_stream);
+        h->pending_theta_out = nullptr;
+        dfree(h, &h->dout);
         free_corpus(h, h->fitc);
         h->fit_open = false;
         return rc;
     }
-    return lda_b200_fit_end(h, theta_out);
+    rc = lda_b200_fit_end(h, theta_out);
+    h->pending_theta_out = nullptr;
+    return rc;
 }
 
 // ---- Transform / Perplexity / Components -----------------------------------------------------------------
