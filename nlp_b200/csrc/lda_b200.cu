@@ -47,13 +47,13 @@ struct Corpus {
     float *theta = nullptr;
     int *order = nullptr;  // documents of each launch range, longest first (order inside a minibatch is free:
                            // documents only interact through commutative sums)
-    double n_local = 0;  // sum of values of the local shard
-    double n_global = 0;
+    double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
 };
 
 struct EventPair {
     cudaEvent_t a, b;
-    int kind;  // 0 = minibatch kernel, 1 = blend kernel, 2 = all-reduce (includes waiting for the slowest rank)
+    int kind;  // 0 = minibatch kernel, 1 = M-step kernels, 2 = exchange (all-reduce or peer kernel; includes the wait
+               // for the slowest rank)
 };
 
 }  // namespace
@@ -79,7 +79,6 @@ struct lda_b200_handle {
     double *nzhat = nullptr;
     double *colsum = nullptr;
     float *inv_colsum = nullptr;
-    unsigned *ticket = nullptr;
     int *doc_counter = nullptr;
     int *err_flag = nullptr;
     double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
@@ -873,11 +872,9 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         CU(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t keep = UINT64_MAX;
         CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-        TRY(dalloc(h, &h->ticket, 1));
         TRY(dalloc(h, &h->doc_counter, 1));
         TRY(dalloc(h, &h->err_flag, 1));
         TRY(dalloc(h, &h->dacc, 2));
-        CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
         h->stage_bytes = (size_t)256 << 20;
         CU(cudaMalloc(&h->stage, h->stage_bytes));
@@ -900,6 +897,8 @@ void lda_b200_destroy(lda_b200_handle *h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     peer_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
+    if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    dfree(h, &h->dout);
     free_corpus(h, h->fitc);
     dfree(h, &h->nphi);
     dfree(h, &h->nphi_hat);
@@ -909,7 +908,6 @@ void lda_b200_destroy(lda_b200_handle *h) {
     dfree(h, &h->colsum);
     dfree(h, &h->inv_z);
     dfree(h, &h->inv_colsum);
-    dfree(h, &h->ticket);
     dfree(h, &h->doc_counter);
     dfree(h, &h->err_flag);
     dfree(h, &h->dacc);
@@ -1040,7 +1038,6 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     if (!warm) ctr->rho_phi_t = 1;             // lda.go:497
     CU(cudaMemsetAsync(h->nphi_hat, 0, (size_t)h->W * h->Kp * sizeof(float), h->stream));
     CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
-    CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
     h->it_done = 0;
     h->prev_perplexity = 0;
     h->stopped = false;
