@@ -46,6 +46,7 @@ def parse():
                    help="minibatches in flight per GPU (the reference's Processes / number of GPUs)")
     p.add_argument("--docs", type=int, default=0, help="override the number of documents (debug)")
     p.add_argument("--cpu-docs-per-worker", type=int, default=256)
+    p.add_argument("--cpu-max-threads", type=int, default=64)
     p.add_argument("--e2e-warmup", type=int, default=1, help="untimed FitTransform calls (1 iteration) before the timed one")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
@@ -142,7 +143,8 @@ def cpu_run(args, D, W, K, md, steps, warmup, device):
     the first cores x docs_per_worker documents, one minibatch per worker.  Returns the cpu_baseline dict."""
     import corpus_synth
     from oracle import oracle as O
-    cores = os.cpu_count() or 1
+    # one worker per host core, capped: every worker owns a W x K float64 nPhiHat (205 MB at this shape), lda.go:492-495
+    cores = min(os.cpu_count() or 1, args.cpu_max_threads)
     per = args.cpu_docs_per_worker
     n_docs = min(D, cores * per)
     indptr, ind, data = corpus_synth.generate(n_docs, W, block=args.batch_size, mean_distinct=md, device=device)
