@@ -12,7 +12,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "--expt-relaxed-constexpr",
+    "-shared", "-Xcompiler", "-fPIC,-pthread", "-cudart", "static", "--expt-relaxed-constexpr",
 ]
 
 

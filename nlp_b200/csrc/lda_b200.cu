@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -87,6 +88,14 @@ struct lda_b200_handle {
     void *stage = nullptr;
     size_t stage_bytes = 0;
     double *h_pinned = nullptr;  // small pinned read-back area
+
+    // page-locked staging ring for pageable caller buffers (Go slices, NumPy arrays): host threads copy between the
+    // caller's memory and the ring while the copy engine moves the previous slot
+    static constexpr int kStageSlots = 3;
+    static constexpr size_t kStageSlotBytes = (size_t)64 << 20;
+    void *pin_slot[kStageSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t pin_done[kStageSlots] = {nullptr, nullptr, nullptr};
+    int host_threads = 4;
 
     // streaming of the result during the last iteration of lda_b200_fit (second stream)
     cudaStream_t copy_stream = nullptr;
@@ -571,13 +580,120 @@ std::vector<Segment> make_segments(int64_t D, int64_t b, int rank, int R) {
     return s;
 }
 
+// ---- host <-> device copies that are fast for pageable memory too -----------------------------------------------------
+bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+void threaded_memcpy(void *dst, const void *src, size_t bytes, int threads) {
+    if (bytes < ((size_t)4 << 20) || threads <= 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (bytes / threads + 4095) & ~(size_t)4095;
+    for (int t = 1; t < threads; ++t) {
+        const size_t off = per * t;
+        if (off >= bytes) break;
+        pool.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, std::min(per, bytes - off)); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (std::thread &t : pool) t.join();
+}
+
+int ensure_pin_ring(lda_b200_handle *h) {
+    if (h->pin_slot[0]) return 0;
+    for (int i = 0; i < lda_b200_handle::kStageSlots; ++i) {
+        CU(cudaMallocHost(&h->pin_slot[i], lda_b200_handle::kStageSlotBytes));
+        CU(cudaEventCreateWithFlags(&h->pin_done[i], cudaEventDisableTiming));
+    }
+    h->host_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    return 0;
+}
+
+// host -> device on the handle's stream.  Page-locked sources go straight to the copy engine; pageable ones are
+// copied by host threads into a page-locked ring whose slots are sent asynchronously, so the host copy of slot i+1
+// overlaps the transfer of slot i.
+int h2d(lda_b200_handle *h, void *dst, const void *src, size_t bytes) {
+    if (bytes == 0) return 0;
+    if (!is_pageable(src) || bytes < ((size_t)1 << 20)) {
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        return 0;
+    }
+    TRY(ensure_pin_ring(h));
+    const size_t sb = lda_b200_handle::kStageSlotBytes;
+    int i = 0;
+    for (size_t off = 0; off < bytes; off += sb, ++i) {
+        const int slot = i % lda_b200_handle::kStageSlots;
+        const size_t n = std::min(sb, bytes - off);
+        CU(cudaEventSynchronize(h->pin_done[slot]));  // the slot's previous transfer has left
+        threaded_memcpy(h->pin_slot[slot], (const char *)src + off, n, h->host_threads);
+        CU(cudaMemcpyAsync((char *)dst + off, h->pin_slot[slot], n, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaEventRecord(h->pin_done[slot], h->stream));
+    }
+    return 0;
+}
+
+// device -> host of `rows` rows of `width` bytes (source pitch spitch, destination pitch dpitch); returns after the data
+// is in the caller's memory
+int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+    if (width == 0 || rows == 0) return 0;
+    if (!is_pageable(dst)) {
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    TRY(ensure_pin_ring(h));
+    const size_t sb = lda_b200_handle::kStageSlotBytes;
+    const size_t rows_per = std::max<size_t>(1, sb / width);
+    if (width > sb) {  // very wide rows: let the driver stage them
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
+    struct Pending {
+        int slot;
+        size_t r0, n;
+    };
+    std::vector<Pending> inflight;
+    auto drain_one = [&]() -> int {
+        const Pending p = inflight.front();
+        inflight.erase(inflight.begin());
+        CU(cudaEventSynchronize(h->pin_done[p.slot]));
+        if (dpitch == width) {
+            threaded_memcpy((char *)dst + p.r0 * dpitch, h->pin_slot[p.slot], p.n * width, h->host_threads);
+        } else {
+            for (size_t r = 0; r < p.n; ++r)
+                memcpy((char *)dst + (p.r0 + r) * dpitch, (const char *)h->pin_slot[p.slot] + r * width, width);
+        }
+        return 0;
+    };
+    int i = 0;
+    for (size_t r0 = 0; r0 < rows; r0 += rows_per, ++i) {
+        const int slot = i % lda_b200_handle::kStageSlots;
+        if ((int)inflight.size() == lda_b200_handle::kStageSlots) TRY(drain_one());
+        const size_t n = std::min(rows_per, rows - r0);
+        CU(cudaMemcpy2DAsync(h->pin_slot[slot], width, (const char *)src + r0 * spitch, spitch, width, n, cudaMemcpyDeviceToHost,
+                             h->stream));
+        CU(cudaEventRecord(h->pin_done[slot], h->stream));
+        inflight.push_back({slot, r0, n});
+    }
+    while (!inflight.empty()) TRY(drain_one());
+    return 0;
+}
+
 // copies [R][K] float64 host rows of the given segments into [Dl][Kp] fp32 device rows
 int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const double *src, int K, int Kp, float *dst) {
     const int64_t rows_per_chunk = std::max<int64_t>(1, (int64_t)(h->stage_bytes / sizeof(double)) / K);
     for (const Segment &s : segs) {
         for (int64_t g = s.g0; g < s.g1; g += rows_per_chunk) {
             const int64_t n = std::min(rows_per_chunk, s.g1 - g);
-            CU(cudaMemcpyAsync(h->stage, src + g * K, (size_t)n * K * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+            TRY(h2d(h, h->stage, src + g * K, (size_t)n * K * sizeof(double)));
             pad_rows_kernel<<<grid_for(n * Kp, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage,
                                                                                     dst + (s.l0 + (g - s.g0)) * Kp, n, K, Kp);
             KCHECK();
@@ -631,11 +747,11 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         const int64_t l0 = lp[s.l0];
         for (int64_t p = p0; p < p1; p += chunk) {
             const int64_t n = std::min(chunk, p1 - p);
-            CU(cudaMemcpyAsync(h->stage, ind + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            TRY(h2d(h, h->stage, ind + p, (size_t)n * 8));
             narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, c.ind + l0 + (p - p0), n,
                                                                                   W, h->err_flag);
             KCHECK();
-            CU(cudaMemcpyAsync(h->stage, data + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            TRY(h2d(h, h->stage, data + p, (size_t)n * 8));
             narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage, c.val + l0 + (p - p0), n);
             KCHECK();
         }
@@ -735,18 +851,20 @@ int write_theta_out(lda_b200_handle *h, const Corpus &c, double *theta_out) {
     pt.lap("theta_out: cudaMalloc");
     transpose_out_kernel<true><<<(unsigned)((c.Dl + 31) / 32), 256, 0, h->stream>>>(c.theta, c.Dl, h->K, h->Kp, nullptr, dout, c.Dl);
     h->launches++;
+    int rc = 0;
     cudaError_t e = cudaPeekAtLastError();
     if (e == cudaSuccess) {
         for (const Segment &s : c.segs) {
-            e = cudaMemcpy2DAsync(theta_out + s.g0, (size_t)c.D * sizeof(double), dout + s.l0, (size_t)c.Dl * sizeof(double),
-                                  (size_t)(s.g1 - s.g0) * sizeof(double), (size_t)h->K, cudaMemcpyDeviceToHost, h->stream);
-            if (e != cudaSuccess) break;
+            rc = d2h_2d(h, theta_out + s.g0, (size_t)c.D * sizeof(double), dout + s.l0, (size_t)c.Dl * sizeof(double),
+                        (size_t)(s.g1 - s.g0) * sizeof(double), (size_t)h->K);
+            if (rc) break;
         }
     }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    if (e == cudaSuccess && !rc) e = cudaStreamSynchronize(h->stream);
     pt.lap("theta_out: normalise + D2H");
     cudaFreeAsync(dout, h->stream);
     pt.lap("theta_out: free");
+    if (rc) return rc;
     if (e != cudaSuccess) return fail(h, LDA_B200_ECUDA, "theta read-back failed: %s", cudaGetErrorString(e));
     return 0;
 }
@@ -918,6 +1036,10 @@ void lda_b200_destroy(lda_b200_handle *h) {
     for (EventPair &p : h->ev_pool) {
         cudaEventDestroy(p.a);
         cudaEventDestroy(p.b);
+    }
+    for (int i = 0; i < lda_b200_handle::kStageSlots; ++i) {
+        if (h->pin_slot[i]) cudaFreeHost(h->pin_slot[i]);
+        if (h->pin_done[i]) cudaEventDestroy(h->pin_done[i]);
     }
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -1101,7 +1223,8 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
         ctr->rho_theta_t += 1;  // lda.go:502
         TRY(fill_rho_table(h, ctr->rho_theta_t, B + 1));
         // last iteration of lda_b200_fit: stream the result out behind every launch
-        const bool stream_out = h->pending_theta_out && h->it_done + 1 == cfg.iterations && c.Dl > 0;
+        const bool stream_out = h->pending_theta_out && h->it_done + 1 == cfg.iterations && c.Dl > 0 &&
+                                !is_pageable(h->pending_theta_out);
         if (stream_out) {
             TRY(dalloc(h, &h->dout, (size_t)h->K * c.Dl));
             h->theta_streamed = true;
@@ -1517,11 +1640,11 @@ int lda_b200_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t 
         const int64_t chunk = (int64_t)(h->stage_bytes / 8);
         for (int64_t p = 0; p < nnz; p += chunk) {
             const int64_t n = std::min(chunk, nnz - p);
-            CU(cudaMemcpyAsync(h->stage, col_ind + p, (size_t)n * 8, cudaMemcpyHostToDevice, h->stream));
+            TRY(h2d(h, h->stage, col_ind + p, (size_t)n * 8));
             narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, d_cols + p, n, D, h->err_flag);
             KCHECK();
         }
-        CU(cudaMemcpyAsync(d_data, data, (size_t)nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        TRY(h2d(h, d_data, data, (size_t)nnz * sizeof(double)));
         if (nnz > 0) {
             csr_expand_rows_kernel<<<grid_for(W * 32, 256, h->sms * 8), 256, 0, h->stream>>>(d_rowptr, W, d_rows);
             KCHECK();
