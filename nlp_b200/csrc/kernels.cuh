@@ -887,11 +887,15 @@ __global__ void __launch_bounds__(256) transpose_out_kernel(const float *src, in
 }
 
 // ---- ingestion -------------------------------------------------------------------------------------
-// int64 word ids -> int32 (exact; ids outside [0,W) raise *err), float64 values -> fp32
+// int64 word ids -> int32 (exact); an id outside [0,W) raises *err and is stored as 0 so that kernels which already run
+// on the data stay inside nPhi -- the call then fails with LDA_B200_EINVAL.  float64 values -> fp32.
 __global__ void narrow_ind_kernel(const int64_t *src, int32_t *dst, int64_t n, int64_t W, int *err) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t w = src[i];
-        if (w < 0 || w >= W) *err = 1;
+        int64_t w = src[i];
+        if (w < 0 || w >= W) {
+            *err = 1;
+            w = 0;
+        }
         dst[i] = (int32_t)w;
     }
 }

@@ -48,6 +48,10 @@ struct Corpus {
     float *theta = nullptr;
     int *order = nullptr;  // documents of each launch range, longest first (order inside a minibatch is free:
                            // documents only interact through commutative sums)
+    // word ids may still be arriving on the copy stream during the first iteration of lda_b200_fit: one event per launch
+    // range, recorded when that range's ids are in place
+    std::vector<cudaEvent_t> range_ev;
+    bool ind_deferred = false;
     double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
 };
 
@@ -214,6 +218,8 @@ void dfree(lda_b200_handle *h, T **p) {
 }
 
 void free_corpus(lda_b200_handle *h, Corpus &c) {
+    if (c.ind_deferred && h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    for (cudaEvent_t e : c.range_ev) cudaEventDestroy(e);
     dfree(h, &c.doc_ptr);
     dfree(h, &c.ind);
     dfree(h, &c.val);
@@ -619,10 +625,11 @@ int ensure_pin_ring(lda_b200_handle *h) {
 // host -> device on the handle's stream.  Page-locked sources go straight to the copy engine; pageable ones are
 // copied by host threads into a page-locked ring whose slots are sent asynchronously, so the host copy of slot i+1
 // overlaps the transfer of slot i.
-int h2d(lda_b200_handle *h, void *dst, const void *src, size_t bytes) {
+int h2d(lda_b200_handle *h, void *dst, const void *src, size_t bytes, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     if (bytes == 0) return 0;
     if (!is_pageable(src) || bytes < ((size_t)1 << 20)) {
-        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
         return 0;
     }
     TRY(ensure_pin_ring(h));
@@ -633,8 +640,8 @@ int h2d(lda_b200_handle *h, void *dst, const void *src, size_t bytes) {
         const size_t n = std::min(sb, bytes - off);
         CU(cudaEventSynchronize(h->pin_done[slot]));  // the slot's previous transfer has left
         threaded_memcpy(h->pin_slot[slot], (const char *)src + off, n, h->host_threads);
-        CU(cudaMemcpyAsync((char *)dst + off, h->pin_slot[slot], n, cudaMemcpyHostToDevice, h->stream));
-        CU(cudaEventRecord(h->pin_done[slot], h->stream));
+        CU(cudaMemcpyAsync((char *)dst + off, h->pin_slot[slot], n, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(h->pin_done[slot], st));
     }
     return 0;
 }
@@ -704,7 +711,8 @@ int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const doub
 
 // Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
 int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                  const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order) {
+                  const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order,
+                  bool defer_ind = false) {
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
     PhaseTimer pt(h->stream);
@@ -742,20 +750,34 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     pt.lap("ingest: cudaMalloc corpus");
 
     const int64_t chunk = (int64_t)(h->stage_bytes / 8);
+    // values first: wc and wordsInCorpus (needed by the first M-step) depend only on them
     for (const Segment &s : c.segs) {
         const int64_t p0 = indptr[s.g0], p1 = indptr[s.g1];
         const int64_t l0 = lp[s.l0];
         for (int64_t p = p0; p < p1; p += chunk) {
             const int64_t n = std::min(chunk, p1 - p);
-            TRY(h2d(h, h->stage, ind + p, (size_t)n * 8));
-            narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, c.ind + l0 + (p - p0), n,
-                                                                                  W, h->err_flag);
-            KCHECK();
             TRY(h2d(h, h->stage, data + p, (size_t)n * 8));
             narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage, c.val + l0 + (p - p0), n);
             KCHECK();
         }
     }
+    // word ids of the local documents [la, lb): host slices of the owning segments -> c.ind, on stream st
+    auto upload_ind = [&](int64_t la, int64_t lb, cudaStream_t st) -> int {
+        for (const Segment &s : c.segs) {
+            const int64_t a = std::max(la, s.l0), b = std::min(lb, s.l0 + (s.g1 - s.g0));
+            if (a >= b) continue;
+            const int64_t p0 = indptr[s.g0 + (a - s.l0)], p1 = indptr[s.g0 + (b - s.l0)];
+            for (int64_t p = p0; p < p1; p += chunk) {
+                const int64_t n = std::min(chunk, p1 - p);
+                TRY(h2d(h, h->stage, ind + p, (size_t)n * 8, st));
+                narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const int64_t *)h->stage, c.ind + lp[a] + (p - p0), n, W,
+                                                                               h->err_flag);
+                KCHECK();
+            }
+        }
+        return 0;
+    };
+    if (!defer_ind) TRY(upload_ind(0, Dl, h->stream));
     {   // Longest-first processing order inside every launch range (`conc` minibatches for Fit, everything for
         // Transform), by a stable counting sort on the document length; runs on the host while the copies above are
         // in flight.
@@ -790,6 +812,22 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     int bad;
     memcpy(&bad, h->h_pinned + 1, sizeof(int));
     if (bad) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)W);
+    if (defer_ind) {
+        // The stage buffer now belongs to the copy stream: the ids of launch range r (conc minibatches) are sent, narrowed
+        // and signalled with range_ev[r]; the first iteration's launches wait on their own range only.
+        const int64_t blk = c.b * c.conc;
+        CU(cudaEventRecord(h->copy_ev, h->stream));
+        CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
+        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
+            TRY(upload_ind(l0, std::min(Dl, l0 + blk), h->copy_stream));
+            cudaEvent_t e;
+            CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c.range_ev.push_back(e);
+            CU(cudaEventRecord(e, h->copy_stream));
+        }
+        c.ind_deferred = true;
+        pt.lap("ingest: word ids queued on the copy stream");
+    }
     return 0;
 }
 
@@ -1105,7 +1143,7 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
 // ---- FitTransform, lda.go:463-542 ----------------------------------------------------------------------
 static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                           const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
-                          lda_b200_counters *ctr, bool warm) {
+                          lda_b200_counters *ctr, bool warm, bool defer_ind = false) {
     if (!h) return LDA_B200_EINVAL;
     if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
     if (warm && (!h->fitted || h->W != W))
@@ -1149,7 +1187,8 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     TRY(refresh_inv_z(h));
     pt.lap("fit_begin: model alloc + nPhi init");
 
-    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true));
+    // (explicit ntheta0 rows are uploaded through the same stage buffer the deferred ids would occupy)
+    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true, defer_ind && ntheta0 == nullptr));
     pt.t0 = PhaseTimer::now();
     TRY(init_theta(h, h->fitc, ntheta0, rnd, draws));
     pt.lap("fit_begin: nTheta init");
@@ -1181,7 +1220,7 @@ int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t
                          int32_t iterations, double *theta_out) {
     if (!h) return LDA_B200_EINVAL;
     const bool warm = h->fitted;
-    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nullptr, ntheta0, rnd, ctr, warm));
+    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nullptr, ntheta0, rnd, ctr, warm, iterations > 0));
     const int32_t saved_it = h->cfg.iterations, saved_f = h->cfg.perplexity_evaluation_frequency;
     h->cfg.iterations = iterations;
     h->cfg.perplexity_evaluation_frequency = 0;
@@ -1252,6 +1291,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             if (l_first >= 0) {
                 a.doc_begin = (int)(l_first * b);
                 a.doc_end = (int)std::min<int64_t>(c.Dl, (l_last + 1) * b);
+                if (c.ind_deferred) CU(cudaStreamWaitEvent(h->stream, c.range_ev[(size_t)(l_first / c.conc)], 0));
                 int slot;
                 TRY(ev_begin(h, 0, &slot));
                 TRY(launch_docs<true>(h, a, c.order));
@@ -1343,6 +1383,13 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             }
             ctr->rho_phi_t += n_s;  // lda.go:300
         }
+        if (h->fitc.ind_deferred) {  // every range has been waited for; report ids that were out of range
+            h->fitc.ind_deferred = false;
+            int bad = 0;
+            CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            if (bad == 1) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)h->W);
+        }
         h->it_done++;
         ran++;
         const int f = cfg.perplexity_evaluation_frequency;
@@ -1407,7 +1454,8 @@ int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr
                  int32_t *iters_run) {
     if (!h) return LDA_B200_EINVAL;
     PhaseTimer pt(h->stream);
-    TRY(lda_b200_fit_begin(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr));
+    // one call: the caller's arrays stay valid until it returns, so the word ids may stream in behind the first launches
+    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr, false, h->cfg.iterations > 0));
     pt.lap("fit: begin total");
     h->pending_theta_out = theta_out;
     h->theta_streamed = false;
