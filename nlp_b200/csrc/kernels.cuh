@@ -574,6 +574,9 @@ struct FusedArgs {
     double *nzhat_local;     // [Kp] this rank's partial column sums (zero on entry)
 };
 
+// U rows per thread and iteration: with few ranks a thread has few peer loads of its own, and U independent rows keep
+// enough bytes in flight on NVLink (U * R * 16 B per thread); RMAX >= R bounds the register arrays.
+template <int U, int RMAX>
 __global__ void __launch_bounds__(256) peer_reduce_blend_kernel(const FusedArgs a) {
     extern __shared__ float4 sm4[];
     const int R = a.pt.nranks, me = a.pt.rank;
@@ -581,34 +584,50 @@ __global__ void __launch_bounds__(256) peer_reduce_blend_kernel(const FusedArgs 
     const int RPB = blockDim.x / VPR;
     const int col = threadIdx.x % VPR;
     const int rslot = threadIdx.x / VPR;
+    const int64_t stride = (int64_t)gridDim.x * RPB;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t r = a.row0 + (int64_t)blockIdx.x * RPB + rslot; r < a.row1; r += (int64_t)gridDim.x * RPB) {
-        const int64_t e = r * VPR + col;  // float4 index
-        float4 h[MAX_PEERS];
+    for (int64_t r0 = a.row0 + (int64_t)blockIdx.x * RPB + rslot; r0 < a.row1; r0 += stride * U) {
+        float4 h[U][RMAX];
+        float4 p[U];
 #pragma unroll
-        for (int q = 0; q < MAX_PEERS; ++q)
-            if (q < R) h[q] = reinterpret_cast<const float4 *>(a.pt.hat[a.cur][q])[e];  // all peer loads in flight
-        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            if (r < a.row1) {
+                const int64_t e = r * VPR + col;  // float4 index
 #pragma unroll
-        for (int q = 0; q < MAX_PEERS; ++q)
-            if (q < R) {
-                sum.x += h[q].x;
-                sum.y += h[q].y;
-                sum.z += h[q].z;
-                sum.w += h[q].w;
+                for (int q = 0; q < RMAX; ++q)
+                    if (q < R) h[u][q] = reinterpret_cast<const float4 *>(a.pt.hat[a.cur][q])[e];  // all peer loads in flight
+                p[u] = reinterpret_cast<const float4 *>(a.pt.nphi[me])[e];
             }
-        float4 p = reinterpret_cast<const float4 *>(a.pt.nphi[me])[e];
-        p.x = fmaf(a.A, p.x, a.C * sum.x);
-        p.y = fmaf(a.A, p.y, a.C * sum.y);
-        p.z = fmaf(a.A, p.z, a.C * sum.z);
-        p.w = fmaf(a.A, p.w, a.C * sum.w);
+        }
 #pragma unroll
-        for (int q = 0; q < MAX_PEERS; ++q)
-            if (q < R) reinterpret_cast<float4 *>(a.pt.nphi[q])[e] = p;
-        acc.x += sum.x;
-        acc.y += sum.y;
-        acc.z += sum.z;
-        acc.w += sum.w;
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            if (r < a.row1) {
+                const int64_t e = r * VPR + col;
+                float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q)
+                    if (q < R) {
+                        sum.x += h[u][q].x;
+                        sum.y += h[u][q].y;
+                        sum.z += h[u][q].z;
+                        sum.w += h[u][q].w;
+                    }
+                float4 v = p[u];
+                v.x = fmaf(a.A, v.x, a.C * sum.x);
+                v.y = fmaf(a.A, v.y, a.C * sum.y);
+                v.z = fmaf(a.A, v.z, a.C * sum.z);
+                v.w = fmaf(a.A, v.w, a.C * sum.w);
+#pragma unroll
+                for (int q = 0; q < RMAX; ++q)
+                    if (q < R) reinterpret_cast<float4 *>(a.pt.nphi[q])[e] = v;
+                acc.x += sum.x;
+                acc.y += sum.y;
+                acc.z += sum.z;
+                acc.w += sum.w;
+            }
+        }
     }
     // zero the buffer the next step accumulates into (its readers finished at the previous step's closing barrier)
     {

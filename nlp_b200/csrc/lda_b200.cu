@@ -1331,7 +1331,12 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 fa.C = (float)Cd;
                 fa.nzhat_local = h->nzhat;
                 const int bs = blend_block(h->Kp);
-                peer_reduce_blend_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                if (R <= 2)
+                    peer_reduce_blend_kernel<4, 2><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                else if (R <= 4)
+                    peer_reduce_blend_kernel<2, 4><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                else
+                    peer_reduce_blend_kernel<1, 8><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 KCHECK();
                 bar.finish = 1;
                 bar.epoch = ++h->epoch;
