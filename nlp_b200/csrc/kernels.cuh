@@ -922,10 +922,6 @@ __global__ void narrow_val_kernel(const double *src, float *dst, int64_t n) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         dst[i] = (float)src[i];
 }
-__global__ void widen_f32_kernel(const float *src, double *dst, int64_t n) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-        dst[i] = (double)src[i];
-}
 // [R][K] float64 (host layout, lda.go's [r*K+k]) <-> [R][Kp] fp32 with zero pad
 __global__ void pad_rows_kernel(const double *src, float *dst, int64_t R, int K, int Kp) {
     const int64_t n = R * Kp;

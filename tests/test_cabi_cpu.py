@@ -182,3 +182,22 @@ def test_model_serialisation_round_trip():
         deserialise_model(buf[:100])
     with pytest.raises(ValueError):
         deserialise_model(b"\x00" * 200)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    # the driver's contract: exactly one JSON line on stdout; the reference arm runs on host cores only
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1",
+                        "--steps", "1", "--warmup", "0", "--cpu-docs-per-worker", "64"], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [x for x in r.stdout.splitlines() if x.strip()]
+    assert len(lines) == 1
+    j = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in j, key
+    assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["value"] > 0
+    assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
