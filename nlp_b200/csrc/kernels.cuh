@@ -275,9 +275,9 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     const int lane = threadIdx.x & 31;
     float4 *ring = ring_all + (threadIdx.x >> 5) * (R * NV * 32) + lane;  // slot s, slice v: ring[(s*NV+v)*32]
     const int Kp = FULLK ? 128 * NV : a.Kp;
-    const unsigned row_bytes = 4u * (unsigned)Kp;   // W*Kp*4 < 2^32 is checked by the host
-    unsigned lane_bytes = 16u * (unsigned)lane;
-    asm volatile("" : "+r"(lane_bytes));  // keep it in a register: ptxas otherwise re-derives it from %tid per token
+    const unsigned row_vecs = (unsigned)Kp >> 2;  // 32-bit offsets in float4 units: W*Kp/4 < 2^32 is checked by the host
+    unsigned lane_vec = (unsigned)lane;
+    asm volatile("" : "+r"(lane_vec));  // keep it in a register: ptxas otherwise re-derives it from %tid per token
     const float alpha = a.alpha;
     const char *__restrict__ cmat_b = reinterpret_cast<const char *>(a.cmat);
     const int32_t *__restrict__ ind = a.ind;
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     // asynchronous copy of this lane's slices of row w into ring slot `slot`; always closes one cp.async group
     auto issue = [&](int slot, int w) {
         if (w >= 0) {
-            const char *src = cmat_b + ((unsigned)w * row_bytes + lane_bytes);
+            const char *src = cmat_b + (size_t)((unsigned)w * row_vecs + lane_vec) * 16u;
 #pragma unroll
             for (int v = 0; v < NV; ++v)
                 if (ok[v]) cp_async16(ring + (slot * NV + v) * 32, reinterpret_cast<const float *>(src + 512 * v));
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                 if (MAINP) {
                     const int w = __shfl_sync(FULL, cur.wi, t);
                     const float sc = hat_scale * r;
-                    float *hp = reinterpret_cast<float *>(reinterpret_cast<char *>(a.nphi_hat) + ((unsigned)w * row_bytes + lane_bytes));
+                    float *hp = reinterpret_cast<float *>(reinterpret_cast<char *>(a.nphi_hat) + (size_t)((unsigned)w * row_vecs + lane_vec) * 16u);
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
                         if (ok[v])

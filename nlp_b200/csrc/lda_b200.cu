@@ -365,8 +365,8 @@ int ensure_model(lda_b200_handle *h, int64_t W) {
     if (h->W == W && h->K == K && h->nphi) return 0;
     if (W < 1) return fail(h, LDA_B200_EINVAL, "matrix has no rows (W = %lld)", (long long)W);
     if (W > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "W = %lld exceeds int32 word ids", (long long)W);
-    if ((uint64_t)W * (uint64_t)Kp * 4u >= (1ull << 32))
-        return fail(h, LDA_B200_EUNSUPPORTED, "nPhi of %lld x %d floats exceeds the 4 GB the kernels address with 32-bit offsets", (long long)W, K);
+    if ((uint64_t)W * (uint64_t)Kp / 4u >= (1ull << 32))
+        return fail(h, LDA_B200_EUNSUPPORTED, "nPhi of %lld x %d floats exceeds the 64 GB the kernels address with 32-bit float4 offsets", (long long)W, K);
     peer_teardown(h);
     h->W = W;
     h->K = K;
