@@ -463,3 +463,36 @@ def test_medium_parity():
     m = CSC(20000, 1000, indptr, ind, data)
     lda, o = run_pair(m, 100, 3, BatchSize=256)
     print("medium parity: rel perplexity delta", np.abs(np.array(lda.PerplexityTrace) / o.perplexity_trace - 1).max())
+
+
+def _full_size_properties(name, batch, processes, iters):
+    import torch
+    D, W, K, md = corpus_synth.shape(name)
+    indptr, ind, data = corpus_synth.generate(D, W, block=8192, mean_distinct=md, device=torch.device("cuda", 0))
+    m = CSC(W, D, indptr, ind, data)
+    lda = new_lda(K, Iterations=iters, BatchSize=batch, Processes=processes, PerplexityEvaluationFrequency=5,
+                  PerplexityTolerance=0.0)
+    theta = lda.FitTransform(m)
+    assert theta.shape == (K, D) and np.isfinite(theta).all() and theta.min() >= 0
+    assert np.abs(1 - theta.sum(axis=0)).max() <= 1e-8            # lda_test.go:172 at scale
+    assert lda.wordsInCorpus == float(data.sum())                  # lda.go:476-482
+    tr = np.array(lda.PerplexityTrace)
+    print(name, "perplexity every 5 iterations", np.round(tr, 1).tolist())
+    # from a random init the training perplexity first rises for a few iterations; it must be falling by the end
+    assert len(tr) == iters // 5 and np.isfinite(tr).all() and tr[-1] < tr[-2] and tr[-1] < tr.max(), tr
+    nphi, nz = lda.GetState()
+    assert np.isfinite(nphi).all() and nphi.min() >= 0
+    # invariant of the algorithm: nZ[k] == sum_w nPhi[w,k] (lda.go:203, then Eqn 7 and 8 are the same affine map)
+    np.testing.assert_allclose(nz, nphi.sum(axis=0), rtol=2e-4)
+    comp = lda.Components()
+    assert comp.shape == (K, W) and np.abs(1 - comp.sum(axis=1)).max() <= 1e-8   # lda_test.go:84 at scale
+
+
+def test_config3_properties_full_size():
+    """configs[2] at full size: 1M docs x 100k vocab, K=256, ~200M non-zeros"""
+    _full_size_properties("C3", 8192, 4, 20)
+
+
+def test_config4_properties_full_size():
+    """configs[3] at full size: 200k docs x 100k vocab, K=1024 (nPhi 410 MB, beyond L2)"""
+    _full_size_properties("C4", 2048, 4, 20)  # 25 M-steps per iteration: past the initial transient by iteration 20
