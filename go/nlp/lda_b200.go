@@ -125,24 +125,46 @@ func (l *LatentDirichletAllocation) Close() {
 	}
 }
 
-// toCSC is lda.go:464-466 plus the dense branch of ColNonZeroElemDo (utils.go:51-57): rows ascending, zeros skipped.
-func toCSC(m mat.Matrix) (r, c int, indptr, ind []int, data []float64) {
-	if t, ok := m.(sparse.TypeConverter); ok {
-		csc := t.ToCSC()
-		r, c = csc.Dims()
-		raw := csc.RawMatrix() // Indptr, Ind []int ; Data []float64 -- Go int == int64 on amd64
-		return r, c, raw.Indptr, raw.Ind, raw.Data
+// matrix describes m to the library in the storage it already has, so that ToCSC() (lda.go:464-466) and the dense
+// scan of ColNonZeroElemDo (utils.go:51-57) run on the GPU instead of on one host thread:
+//   *sparse.CSR (what TfidfTransformer emits, weightings.go:79-95) -> LDA_B200_CSR, zero copy
+//   *sparse.CSC                                                      -> LDA_B200_CSC, zero copy
+//   *mat.Dense with Stride == cols                                  -> LDA_B200_DENSE, zero copy
+//   any other sparse.TypeConverter (DOK, COO, ...)                   -> ToCSC() on the host, then LDA_B200_CSC
+//   any other mat.Matrix                                             -> copied into a dense buffer, LDA_B200_DENSE
+// keep holds the Go slices the descriptor points into; the caller passes it to runtime.KeepAlive after the C call.
+func matrix(m mat.Matrix) (desc C.lda_b200_matrix, keep []interface{}) {
+	r, c := m.Dims()
+	desc.rows, desc.cols = C.int64_t(r), C.int64_t(c)
+	sparseDesc := func(format C.int32_t, indptr, ind []int, data []float64) {
+		desc.format = format
+		desc.ptr, desc.ind, desc.data = ptrI(indptr), ptrI(ind), ptrF(data) // Go int == int64 on amd64
+		keep = []interface{}{indptr, ind, data}
 	}
-	r, c = m.Dims()
-	indptr = make([]int, c+1)
-	for j := 0; j < c; j++ {
-		for i := 0; i < r; i++ {
-			if v := m.At(i, j); v != 0 {
-				ind = append(ind, i)
-				data = append(data, v)
+	switch t := m.(type) {
+	case *sparse.CSR:
+		raw := t.RawMatrix()
+		sparseDesc(C.LDA_B200_CSR, raw.Indptr, raw.Ind, raw.Data)
+	case *sparse.CSC:
+		raw := t.RawMatrix()
+		sparseDesc(C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data)
+	case sparse.TypeConverter:
+		raw := t.ToCSC().RawMatrix()
+		sparseDesc(C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data)
+	default:
+		var data []float64
+		if d, ok := m.(*mat.Dense); ok && d.RawMatrix().Stride == c {
+			data = d.RawMatrix().Data
+		} else {
+			data = make([]float64, r*c)
+			for i := 0; i < r; i++ {
+				for j := 0; j < c; j++ {
+					data[i*c+j] = m.At(i, j)
+				}
 			}
 		}
-		indptr[j+1] = len(ind)
+		desc.format, desc.data = C.LDA_B200_DENSE, ptrF(data)
+		keep = []interface{}{data}
 	}
 	return
 }
@@ -188,7 +210,8 @@ func (l *LatentDirichletAllocation) fit(m mat.Matrix, want bool) (mat.Matrix, er
 	if err != nil {
 		return nil, err
 	}
-	r, c, indptr, ind, data := toCSC(m)
+	desc, keep := matrix(m)
+	r, c := m.Dims()
 	l.w, l.d = r, c
 	var theta []float64
 	if want {
@@ -196,11 +219,8 @@ func (l *LatentDirichletAllocation) fit(m mat.Matrix, want bool) (mat.Matrix, er
 	}
 	ctr := C.lda_b200_counters{rho_phi_t: C.double(l.rhoPhiT), rho_theta_t: C.double(l.rhoThetaT), words_in_corpus: C.double(l.wordsInCorpus)}
 	rnd := l.pcg()
-	rc := C.lda_b200_fit(h, C.int64_t(r), C.int64_t(c), ptrI(indptr), ptrI(ind), ptrF(data), nil, nil, &rnd, &ctr,
-		ptrF(theta), nil, 0, nil, nil)
-	runtime.KeepAlive(indptr)
-	runtime.KeepAlive(ind)
-	runtime.KeepAlive(data)
+	rc := C.lda_b200_fit_matrix(h, &desc, nil, nil, &rnd, &ctr, ptrF(theta), nil, 0, nil, nil)
+	runtime.KeepAlive(keep)
 	if rc != 0 {
 		return nil, l.err()
 	}
@@ -218,11 +238,13 @@ func (l *LatentDirichletAllocation) Transform(m mat.Matrix) (mat.Matrix, error) 
 	if err != nil {
 		return nil, err
 	}
-	_, c, indptr, ind, data := toCSC(m)
+	desc, keep := matrix(m)
+	_, c := m.Dims()
 	theta := make([]float64, l.K*c)
 	rnd := l.pcg()
-	if rc := C.lda_b200_transform(h, C.int64_t(c), ptrI(indptr), ptrI(ind), ptrF(data), nil, &rnd,
-		C.double(l.rhoThetaT), ptrF(theta), nil); rc != 0 {
+	rc := C.lda_b200_transform_matrix(h, &desc, nil, &rnd, C.double(l.rhoThetaT), ptrF(theta), nil)
+	runtime.KeepAlive(keep)
+	if rc != 0 {
 		return nil, l.err()
 	}
 	l.takePcg(rnd)
@@ -235,11 +257,12 @@ func (l *LatentDirichletAllocation) Perplexity(m mat.Matrix) float64 {
 	if err != nil {
 		panic(err)
 	}
-	_, c, indptr, ind, data := toCSC(m)
+	desc, keep := matrix(m)
 	rnd := l.pcg()
 	var out C.double
-	if rc := C.lda_b200_perplexity(h, C.int64_t(c), ptrI(indptr), ptrI(ind), ptrF(data), nil, &rnd,
-		C.double(l.rhoThetaT), &out); rc != 0 {
+	rc := C.lda_b200_perplexity_matrix(h, &desc, nil, &rnd, C.double(l.rhoThetaT), &out)
+	runtime.KeepAlive(keep)
+	if rc != 0 {
 		panic(l.err())
 	}
 	l.takePcg(rnd)

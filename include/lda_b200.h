@@ -83,6 +83,27 @@ typedef struct {
     uint64_t high, low;
 } lda_b200_pcg;
 
+/* The `mat.Matrix` argument of Fit / FitTransform / Transform / Perplexity (term x document: rows = words W,
+ * cols = documents D) in the storage the Go value already has, so the shim need not call ToCSC() (lda.go:464-466)
+ * or scan a dense matrix (utils.go:51-57) on one host thread: the conversion runs on the device and its result
+ * never returns to the host.
+ *  LDA_B200_CSC    ptr = indptr[cols+1], ind = row (word) ids, data = values    (sparse.CSC RawMatrix)
+ *  LDA_B200_CSR    ptr = indptr[rows+1], ind = column (document) ids, data      (sparse.CSR RawMatrix; what the
+ *                  TfidfTransformer hands to the next pipeline step, weightings.go:79-95).  Column ids inside a row
+ *                  need not be sorted; inside a document the words come out in ascending order, as ToCSC() gives.
+ *  LDA_B200_DENSE  data = rows*cols values, row-major (mat.Dense RawMatrix with Stride == cols); ptr = ind = NULL.
+ *                  Exact zeros are skipped, rows ascending inside a document (utils.go:51-57).
+ * With a communicator every rank passes the same whole matrix for CSR / DENSE (each converts it and keeps its own
+ * minibatches); CSC keeps the per-rank-shard convention described above. */
+typedef enum { LDA_B200_CSC = 0, LDA_B200_CSR = 1, LDA_B200_DENSE = 2 } lda_b200_format;
+typedef struct {
+    int32_t format; /* lda_b200_format */
+    int64_t rows, cols;
+    const int64_t *ptr;
+    const int64_t *ind;
+    const double *data;
+} lda_b200_matrix;
+
 typedef struct lda_b200_handle lda_b200_handle;
 
 /* fills the defaults of NewLatentDirichletAllocation(k), lda.go:145-189 */
@@ -151,6 +172,18 @@ int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, con
 int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
                         const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out);
 
+/* The same four calls taking the matrix in its own storage (see lda_b200_matrix); other arguments as above.
+ * Transform / Perplexity fail with LDA_B200_EINVAL when m->rows differs from the fitted model's W. */
+int lda_b200_fit_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *nphi0, const double *ntheta0,
+                        lda_b200_pcg *rnd, lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap,
+                        int32_t *n_evals, int32_t *iters_run);
+int lda_b200_partial_fit_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *ntheta0, lda_b200_pcg *rnd,
+                                lda_b200_counters *ctr, int32_t iterations, double *theta_out);
+int lda_b200_transform_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                              double rho_theta_t, double *theta_out, int32_t *passes_out);
+int lda_b200_perplexity_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                               double rho_theta_t, double *out);
+
 /* Components, lda.go:414-416: out = K*W doubles */
 int lda_b200_components(lda_b200_handle *h, double *out);
 
@@ -173,6 +206,11 @@ void lda_b200_pcg_advance(lda_b200_pcg *rnd, uint64_t draws);
 int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                               const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
                               double *wc_out, double *n_out);
+
+/* The same for a matrix in its own storage: what the *_matrix calls hold on the device after the device-side
+ * conversion.  Call once with only nnz_out to size the arrays (indptr_out cols+1, ind_out / val_out nnz, wc_out cols). */
+int lda_b200_ingest_roundtrip_matrix(lda_b200_handle *h, const lda_b200_matrix *m, int64_t *nnz_out, int64_t *indptr_out,
+                                     int32_t *ind_out, float *val_out, double *wc_out, double *n_out);
 
 /* sparse.ToCSC() (lda.go:464-466) of a CSR term x document matrix, on the device: row_ptr[W+1], col_ind[nnz]
  * (document ids), data[nnz] -> indptr_out[D+1], ind_out[nnz] (word ids, ascending inside a document), data_out[nnz].

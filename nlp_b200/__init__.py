@@ -3,6 +3,6 @@
 Only the hot path is here: `LatentDirichletAllocation` with `Fit` / `FitTransform` /
 `Transform` / `Perplexity` / `Components`, computed by hand-written sm_100a kernels in liblda_b200.so.
 """
-from .lda import (CSC, LatentDirichletAllocation, LearningSchedule,  # noqa: F401
+from .lda import (CSC, CSR, LatentDirichletAllocation, LearningSchedule,  # noqa: F401
                   NewLatentDirichletAllocation)
 from . import rand  # noqa: F401

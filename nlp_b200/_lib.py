@@ -29,6 +29,14 @@ class Pcg(C.Structure):
     _fields_ = [("high", C.c_uint64), ("low", C.c_uint64)]
 
 
+class Matrix(C.Structure):
+    """lda_b200_matrix"""
+    _fields_ = [("format", C.c_int32), ("rows", C.c_int64), ("cols", C.c_int64), ("ptr", C.c_void_p), ("ind", C.c_void_p),
+                ("data", C.c_void_p)]
+
+
+FORMAT_CSC, FORMAT_CSR, FORMAT_DENSE = 0, 1, 2
+
 # every symbol include/lda_b200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -48,6 +56,11 @@ SYMBOLS = {
                                        C.c_int32, _P]),
     "lda_b200_transform": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, _P, _P]),
     "lda_b200_perplexity": (C.c_int, [_P, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, C.POINTER(C.c_double)]),
+    "lda_b200_fit_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, _P, C.POINTER(Pcg), C.POINTER(Counters), _P, _P, C.c_int32,
+                                      C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "lda_b200_partial_fit_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.POINTER(Counters), C.c_int32, _P]),
+    "lda_b200_transform_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.c_double, _P, _P]),
+    "lda_b200_perplexity_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.c_double, C.POINTER(C.c_double)]),
     "lda_b200_components": (C.c_int, [_P, _P]),
     "lda_b200_get_dims": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "lda_b200_get_state": (C.c_int, [_P, _P, _P]),
@@ -57,6 +70,8 @@ SYMBOLS = {
     "lda_b200_pcg_fill": (None, [C.POINTER(Pcg), C.c_int64, C.c_int64, _P]),
     "lda_b200_pcg_advance": (None, [C.POINTER(Pcg), C.c_uint64]),
     "lda_b200_ingest_roundtrip": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_double)]),
+    "lda_b200_ingest_roundtrip_matrix": (C.c_int, [_P, C.POINTER(Matrix), C.POINTER(C.c_int64), _P, _P, _P, _P,
+                                                   C.POINTER(C.c_double)]),
     "lda_b200_csr_to_csc": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, _P]),
     "lda_b200_fit_begin": (C.c_int, [_P, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters)]),
     "lda_b200_fit_iterate": (C.c_int, [_P, C.c_int32, C.POINTER(Counters), _P, C.c_int32, C.POINTER(C.c_int32),

@@ -975,6 +975,31 @@ __global__ void csc_gather_kernel(const uint32_t *perm, const int32_t *rows, con
     }
 }
 
+// ---- dense mat.Matrix -> CSC (ColNonZeroElemDo's dense branch, utils.go:51-57) -------------------------------
+// a is rows x cols row-major; thread j walks column j (adjacent threads read adjacent addresses).  Go's `v != 0`: -0 is
+// skipped, NaN is kept.  cnt has cols+1 entries (the last one 0) so that an exclusive scan yields indptr.
+__global__ void dense_col_count_kernel(const double *a, int64_t W, int64_t D, int64_t *cnt) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= D; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t c = 0;
+        if (j < D)
+            for (int64_t i = 0; i < W; ++i) c += a[i * D + j] != 0.0;
+        cnt[j] = c;
+    }
+}
+__global__ void dense_col_fill_kernel(const double *a, int64_t W, int64_t D, const int64_t *indptr, int64_t *ind, double *data) {
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < D; j += (int64_t)gridDim.x * blockDim.x) {
+        int64_t p = indptr[j];
+        for (int64_t i = 0; i < W; ++i) {
+            const double v = a[i * D + j];
+            if (v != 0.0) {
+                ind[p] = i;
+                data[p] = v;
+                ++p;
+            }
+        }
+    }
+}
+
 // wc[j] = sum of the document's values (lda.go:476-480), float64 accumulation; *n_total += sum_j wc[j] (lda.go:481)
 __global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, const float *val, int n_docs, float *wc,
                                                      double *wc64, double *n_total) {

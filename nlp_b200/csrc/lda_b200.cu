@@ -16,6 +16,7 @@
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 #include "../../include/lda_b200.h"
 #include "kernels.cuh"
@@ -53,6 +54,15 @@ struct Corpus {
     std::vector<cudaEvent_t> range_ev;
     bool ind_deferred = false;
     double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
+};
+
+// a term x document matrix converted to CSC on the device (from CSR or dense input); word ids ascending inside a document
+struct DeviceCSC {
+    int64_t W = 0, D = 0, nnz = 0;
+    int64_t *indptr = nullptr;      // device [D+1]
+    int64_t *ind = nullptr;         // device [nnz]
+    double *data = nullptr;         // device [nnz]
+    std::vector<int64_t> h_indptr;  // host copy of indptr (document lengths drive sharding and the launch order)
 };
 
 struct EventPair {
@@ -710,9 +720,11 @@ int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const doub
 }
 
 // Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
+// src_device: ind / data are device arrays (a matrix converted on the device, see DeviceCSC); indptr is always on the host.
 int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                   const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order,
-                  bool defer_ind = false) {
+                  bool defer_ind = false, bool src_device = false) {
+    if (src_device) defer_ind = false;  // nothing crosses PCIe: no transfer to hide behind the first launches
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
     PhaseTimer pt(h->stream);
@@ -749,15 +761,26 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
     pt.lap("ingest: cudaMalloc corpus");
 
-    const int64_t chunk = (int64_t)(h->stage_bytes / 8);
+    const int64_t chunk = src_device ? ((int64_t)1 << 40) : (int64_t)(h->stage_bytes / 8);
+    // 8-byte source elements [p, p+n) where a kernel can read them: in place for device sources, else through the stage
+    auto staged = [&](const void *src, int64_t p, int64_t n, cudaStream_t st, const void **dev) -> int {
+        if (src_device) {
+            *dev = (const char *)src + p * 8;
+            return 0;
+        }
+        TRY(h2d(h, h->stage, (const char *)src + p * 8, (size_t)n * 8, st));
+        *dev = h->stage;
+        return 0;
+    };
     // values first: wc and wordsInCorpus (needed by the first M-step) depend only on them
     for (const Segment &s : c.segs) {
         const int64_t p0 = indptr[s.g0], p1 = indptr[s.g1];
         const int64_t l0 = lp[s.l0];
         for (int64_t p = p0; p < p1; p += chunk) {
             const int64_t n = std::min(chunk, p1 - p);
-            TRY(h2d(h, h->stage, data + p, (size_t)n * 8));
-            narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)h->stage, c.val + l0 + (p - p0), n);
+            const void *dsrc;
+            TRY(staged(data, p, n, h->stream, &dsrc));
+            narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)dsrc, c.val + l0 + (p - p0), n);
             KCHECK();
         }
     }
@@ -769,8 +792,9 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
             const int64_t p0 = indptr[s.g0 + (a - s.l0)], p1 = indptr[s.g0 + (b - s.l0)];
             for (int64_t p = p0; p < p1; p += chunk) {
                 const int64_t n = std::min(chunk, p1 - p);
-                TRY(h2d(h, h->stage, ind + p, (size_t)n * 8, st));
-                narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const int64_t *)h->stage, c.ind + lp[a] + (p - p0), n, W,
+                const void *dsrc;
+                TRY(staged(ind, p, n, st, &dsrc));
+                narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const int64_t *)dsrc, c.ind + lp[a] + (p - p0), n, W,
                                                                                h->err_flag);
                 KCHECK();
             }
@@ -977,6 +1001,173 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, int32_t *pa
     return rc;
 }
 
+
+// ---- CSR / dense -> CSC on the device (sparse.ToCSC() lda.go:464-466; dense scan utils.go:51-57) -------------------
+void free_device_csc(lda_b200_handle *h, DeviceCSC &m) {
+    dfree(h, &m.indptr);
+    dfree(h, &m.ind);
+    dfree(h, &m.data);
+    m = DeviceCSC();
+}
+
+// The radix sort on the column (document) id is stable, so inside a document the rows stay in ascending order --
+// exactly what the reference's host-side conversion produces and what fixes the token order of the path.
+int device_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *row_ptr, const int64_t *col_ind,
+                      const double *data, DeviceCSC &out) {
+    if (W < 0 || D < 0 || !row_ptr) return fail(h, LDA_B200_EINVAL, "bad CSR arguments");
+    const int64_t nnz = row_ptr[W] - row_ptr[0];
+    if (row_ptr[0] != 0) return fail(h, LDA_B200_EINVAL, "row_ptr[0] must be 0");
+    for (int64_t r = 0; r < W; ++r)
+        if (row_ptr[r + 1] < row_ptr[r]) return fail(h, LDA_B200_EINVAL, "row_ptr is not non-decreasing at row %lld", (long long)r);
+    if (nnz >= (1LL << 31) || D >= (1LL << 31) || W >= (1LL << 31))
+        return fail(h, LDA_B200_EUNSUPPORTED, "CSR with 2^31 or more entries / rows / columns");
+    if (nnz > 0 && (!col_ind || !data)) return fail(h, LDA_B200_EINVAL, "NULL CSR array");
+    int64_t *d_rowptr = nullptr;
+    int32_t *d_cols = nullptr, *d_cols2 = nullptr, *d_rows = nullptr;
+    uint32_t *d_perm = nullptr, *d_perm2 = nullptr;
+    double *d_data = nullptr;
+    void *d_tmp = nullptr;
+    out.W = W;
+    out.D = D;
+    out.nnz = nnz;
+    out.h_indptr.assign((size_t)D + 1, 0);
+    auto run = [&]() -> int {
+        TRY(dalloc(h, &d_rowptr, (size_t)W + 1));
+        TRY(dalloc(h, &out.indptr, (size_t)D + 1));
+        TRY(dalloc(h, &d_cols, (size_t)nnz));
+        TRY(dalloc(h, &d_cols2, (size_t)nnz));
+        TRY(dalloc(h, &d_rows, (size_t)nnz));
+        TRY(dalloc(h, &d_perm, (size_t)nnz));
+        TRY(dalloc(h, &d_perm2, (size_t)nnz));
+        TRY(dalloc(h, &d_data, (size_t)nnz));
+        TRY(dalloc(h, &out.data, (size_t)nnz));
+        TRY(dalloc(h, &out.ind, (size_t)nnz));
+        CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+        const int64_t chunk = (int64_t)(h->stage_bytes / 8);
+        for (int64_t p = 0; p < nnz; p += chunk) {
+            const int64_t n = std::min(chunk, nnz - p);
+            TRY(h2d(h, h->stage, col_ind + p, (size_t)n * 8));
+            narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, d_cols + p, n, D, h->err_flag);
+            KCHECK();
+        }
+        TRY(h2d(h, d_data, data, (size_t)nnz * sizeof(double)));
+        if (nnz > 0) {
+            csr_expand_rows_kernel<<<grid_for(W * 32, 256, h->sms * 8), 256, 0, h->stream>>>(d_rowptr, W, d_rows);
+            KCHECK();
+            iota_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm, nnz);
+            KCHECK();
+            int bits = 1;
+            while ((1LL << bits) < D) ++bits;
+            size_t tmp_bytes = 0;
+            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
+            CU(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, h->stream));
+            CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
+            h->launches += 4;
+            csc_gather_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm2, d_rows, d_data, nnz, out.ind, out.data);
+            KCHECK();
+        }
+        csc_indptr_kernel<<<grid_for(D + 1, 256, h->sms * 8), 256, 0, h->stream>>>(d_cols2, nnz, D, out.indptr);
+        KCHECK();
+        CU(cudaMemcpyAsync(out.h_indptr.data(), out.indptr, ((size_t)D + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        int bad = 0;
+        CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        if (bad) return fail(h, LDA_B200_EINVAL, "a column index lies outside [0, %lld)", (long long)D);
+        return 0;
+    };
+    const int rc = run();
+    dfree(h, &d_rowptr);
+    dfree(h, &d_cols);
+    dfree(h, &d_cols2);
+    dfree(h, &d_rows);
+    dfree(h, &d_perm);
+    dfree(h, &d_perm2);
+    dfree(h, &d_data);
+    if (d_tmp) cudaFreeAsync(d_tmp, h->stream);
+    if (rc) free_device_csc(h, out);
+    return rc;
+}
+
+// dense mat.Matrix (rows x cols, row-major float64): every column lists its non-zero rows in ascending order, entries
+// that are exactly 0 skipped (utils.go:51-57)
+int device_dense_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const double *a, DeviceCSC &out) {
+    if (W < 0 || D < 0) return fail(h, LDA_B200_EINVAL, "bad dense matrix shape");
+    if (W > 0 && D > 0 && !a) return fail(h, LDA_B200_EINVAL, "dense data is NULL");
+    if (W >= (1LL << 31) || D >= (1LL << 31)) return fail(h, LDA_B200_EUNSUPPORTED, "dense matrix with 2^31 or more rows / columns");
+    double *d_a = nullptr;
+    int64_t *d_cnt = nullptr;
+    void *d_tmp = nullptr;
+    out.W = W;
+    out.D = D;
+    out.h_indptr.assign((size_t)D + 1, 0);
+    auto run = [&]() -> int {
+        TRY(dalloc(h, &d_a, (size_t)W * D));
+        TRY(dalloc(h, &d_cnt, (size_t)D + 1));
+        TRY(dalloc(h, &out.indptr, (size_t)D + 1));
+        TRY(h2d(h, d_a, a, (size_t)W * D * sizeof(double)));
+        dense_col_count_kernel<<<grid_for(D + 1, 128, h->sms * 16), 128, 0, h->stream>>>(d_a, W, D, d_cnt);
+        KCHECK();
+        size_t tmp_bytes = 0;
+        CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_cnt, out.indptr, (int)(D + 1), h->stream));
+        CU(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, h->stream));
+        CU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, d_cnt, out.indptr, (int)(D + 1), h->stream));
+        h->launches += 1;
+        CU(cudaMemcpyAsync(out.h_indptr.data(), out.indptr, ((size_t)D + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        out.nnz = out.h_indptr[(size_t)D];
+        TRY(dalloc(h, &out.ind, (size_t)out.nnz));
+        TRY(dalloc(h, &out.data, (size_t)out.nnz));
+        if (out.nnz > 0) {
+            dense_col_fill_kernel<<<grid_for(D, 128, h->sms * 16), 128, 0, h->stream>>>(d_a, W, D, out.indptr, out.ind, out.data);
+            KCHECK();
+        }
+        return 0;
+    };
+    const int rc = run();
+    dfree(h, &d_a);
+    dfree(h, &d_cnt);
+    if (d_tmp) cudaFreeAsync(d_tmp, h->stream);
+    if (rc) free_device_csc(h, out);
+    return rc;
+}
+
+// the caller's matrix as the CSC the path consumes: host arrays as they are (CSC), or converted on the device
+struct MatrixView {
+    int64_t W = 0, D = 0;
+    const int64_t *indptr = nullptr, *ind = nullptr;
+    const double *data = nullptr;
+    bool on_device = false;
+    DeviceCSC owned;
+};
+
+int open_matrix(lda_b200_handle *h, const lda_b200_matrix *m, MatrixView &v) {
+    if (!m) return fail(h, LDA_B200_EINVAL, "matrix is NULL");
+    CU(cudaSetDevice(h->device));
+    v.W = m->rows;
+    v.D = m->cols;
+    switch (m->format) {
+        case LDA_B200_CSC:
+            v.indptr = m->ptr;
+            v.ind = m->ind;
+            v.data = m->data;
+            return 0;
+        case LDA_B200_CSR:
+            TRY(device_csr_to_csc(h, m->rows, m->cols, m->ptr, m->ind, m->data, v.owned));
+            break;
+        case LDA_B200_DENSE:
+            TRY(device_dense_to_csc(h, m->rows, m->cols, m->data, v.owned));
+            break;
+        default:
+            return fail(h, LDA_B200_EINVAL, "unknown matrix format %d", (int)m->format);
+    }
+    v.indptr = v.owned.h_indptr.data();
+    v.ind = v.owned.ind;
+    v.data = v.owned.data;
+    v.on_device = true;
+    return 0;
+}
+
 }  // namespace
 
 // =====================================================================================================
@@ -1143,7 +1334,7 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
 // ---- FitTransform, lda.go:463-542 ----------------------------------------------------------------------
 static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                           const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
-                          lda_b200_counters *ctr, bool warm, bool defer_ind = false) {
+                          lda_b200_counters *ctr, bool warm, bool defer_ind = false, bool src_device = false) {
     if (!h) return LDA_B200_EINVAL;
     if (!ctr) return fail(h, LDA_B200_EINVAL, "counters are NULL");
     if (warm && (!h->fitted || h->W != W))
@@ -1188,7 +1379,7 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     pt.lap("fit_begin: model alloc + nPhi init");
 
     // (explicit ntheta0 rows are uploaded through the same stage buffer the deferred ids would occupy)
-    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true, defer_ind && ntheta0 == nullptr));
+    TRY(upload_corpus(h, h->fitc, W, D, indptr, ind, data, nullptr, true, defer_ind && ntheta0 == nullptr, src_device));
     pt.t0 = PhaseTimer::now();
     TRY(init_theta(h, h->fitc, ntheta0, rnd, draws));
     pt.lap("fit_begin: nTheta init");
@@ -1215,12 +1406,11 @@ int lda_b200_fit_begin(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *
 
 // PartialFit (OnlineTransformer, vectorisers.go:36-39; a TODO for LDA at lda.go:147): `iterations` SCVB0 iterations
 // over the given documents starting from the current nPhi / nZ / rhoPhiT (from a fresh random model on first use).
-int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                         const double *data, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
-                         int32_t iterations, double *theta_out) {
-    if (!h) return LDA_B200_EINVAL;
+static int partial_fit_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                            const double *data, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                            int32_t iterations, double *theta_out, bool src_device) {
     const bool warm = h->fitted;
-    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nullptr, ntheta0, rnd, ctr, warm, iterations > 0));
+    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nullptr, ntheta0, rnd, ctr, warm, iterations > 0, src_device));
     const int32_t saved_it = h->cfg.iterations, saved_f = h->cfg.perplexity_evaluation_frequency;
     h->cfg.iterations = iterations;
     h->cfg.perplexity_evaluation_frequency = 0;
@@ -1233,6 +1423,23 @@ int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t
         return rc;
     }
     return lda_b200_fit_end(h, theta_out);
+}
+
+int lda_b200_partial_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                         const double *data, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                         int32_t iterations, double *theta_out) {
+    if (!h) return LDA_B200_EINVAL;
+    return partial_fit_impl(h, W, D, indptr, ind, data, ntheta0, rnd, ctr, iterations, theta_out, false);
+}
+
+int lda_b200_partial_fit_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *ntheta0, lda_b200_pcg *rnd,
+                                lda_b200_counters *ctr, int32_t iterations, double *theta_out) {
+    if (!h) return LDA_B200_EINVAL;
+    MatrixView v;
+    TRY(open_matrix(h, m, v));
+    const int rc = partial_fit_impl(h, v.W, v.D, v.indptr, v.ind, v.data, ntheta0, rnd, ctr, iterations, theta_out, v.on_device);
+    free_device_csc(h, v.owned);
+    return rc;
 }
 
 int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_counters *ctr, double *perp_trace,
@@ -1453,14 +1660,12 @@ int lda_b200_fit_end(lda_b200_handle *h, double *theta_out) {
     return rc;
 }
 
-int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                 const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
-                 lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
-                 int32_t *iters_run) {
-    if (!h) return LDA_B200_EINVAL;
+static int fit_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                    const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr, double *theta_out,
+                    double *perp_trace, int32_t perp_cap, int32_t *n_evals, int32_t *iters_run, bool src_device) {
     PhaseTimer pt(h->stream);
     // one call: the caller's arrays stay valid until it returns, so the word ids may stream in behind the first launches
-    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr, false, h->cfg.iterations > 0));
+    TRY(fit_begin_impl(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr, false, h->cfg.iterations > 0, src_device));
     pt.lap("fit: begin total");
     h->pending_theta_out = theta_out;
     h->theta_streamed = false;
@@ -1479,16 +1684,35 @@ int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr
     return rc;
 }
 
-// ---- Transform / Perplexity / Components -----------------------------------------------------------------
-int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
-                       const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *theta_out,
-                       int32_t *passes_out) {
+int lda_b200_fit(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                 const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd,
+                 lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals,
+                 int32_t *iters_run) {
     if (!h) return LDA_B200_EINVAL;
+    return fit_impl(h, W, D, indptr, ind, data, nphi0, ntheta0, rnd, ctr, theta_out, perp_trace, perp_cap, n_evals, iters_run, false);
+}
+
+int lda_b200_fit_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *nphi0, const double *ntheta0,
+                        lda_b200_pcg *rnd, lda_b200_counters *ctr, double *theta_out, double *perp_trace, int32_t perp_cap,
+                        int32_t *n_evals, int32_t *iters_run) {
+    if (!h) return LDA_B200_EINVAL;
+    MatrixView v;
+    TRY(open_matrix(h, m, v));
+    const int rc = fit_impl(h, v.W, v.D, v.indptr, v.ind, v.data, nphi0, ntheta0, rnd, ctr, theta_out, perp_trace, perp_cap, n_evals,
+                            iters_run, v.on_device);
+    free_device_csc(h, v.owned);
+    return rc;
+}
+
+// ---- Transform / Perplexity / Components -----------------------------------------------------------------
+static int transform_impl(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                          const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *theta_out, int32_t *passes_out,
+                          bool src_device) {
     if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Transform called before Fit / set_state");
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false);
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device);
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
     if (!rc) rc = run_transform(h, c, rho_theta_t, passes_out);
@@ -1501,20 +1725,61 @@ int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, con
     return rc;
 }
 
-int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
-                        const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out) {
-    if (!h) return LDA_B200_EINVAL;
+static int perplexity_impl(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                           const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out, bool src_device) {
     if (!out) return fail(h, LDA_B200_EINVAL, "out is NULL");
     if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Perplexity called before Fit / set_state");
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false);  // wordCount = c.n_global, lda.go:372-385
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device);  // wordCount = c.n_global, lda.go:372-385
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
     if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr);
     if (!rc) rc = eval_perplexity(h, c, c.n_global, out);
     free_corpus(h, c);
+    return rc;
+}
+
+// a matrix for Transform / Perplexity must have the model's number of rows (the reference would index out of range)
+static int open_model_matrix(lda_b200_handle *h, const lda_b200_matrix *m, MatrixView &v) {
+    if (m && h->fitted && m->rows != h->W)
+        return fail(h, LDA_B200_EINVAL, "matrix has %lld rows, the model was fitted on %lld", (long long)m->rows, (long long)h->W);
+    return open_matrix(h, m, v);
+}
+
+int lda_b200_transform(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                       const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *theta_out,
+                       int32_t *passes_out) {
+    if (!h) return LDA_B200_EINVAL;
+    return transform_impl(h, D, indptr, ind, data, theta0, rnd, rho_theta_t, theta_out, passes_out, false);
+}
+
+int lda_b200_transform_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                              double rho_theta_t, double *theta_out, int32_t *passes_out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Transform called before Fit / set_state");
+    MatrixView v;
+    TRY(open_model_matrix(h, m, v));
+    const int rc = transform_impl(h, v.D, v.indptr, v.ind, v.data, theta0, rnd, rho_theta_t, theta_out, passes_out, v.on_device);
+    free_device_csc(h, v.owned);
+    return rc;
+}
+
+int lda_b200_perplexity(lda_b200_handle *h, int64_t D, const int64_t *indptr, const int64_t *ind, const double *data,
+                        const double *theta0, lda_b200_pcg *rnd, double rho_theta_t, double *out) {
+    if (!h) return LDA_B200_EINVAL;
+    return perplexity_impl(h, D, indptr, ind, data, theta0, rnd, rho_theta_t, out, false);
+}
+
+int lda_b200_perplexity_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                               double rho_theta_t, double *out) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Perplexity called before Fit / set_state");
+    MatrixView v;
+    TRY(open_model_matrix(h, m, v));
+    const int rc = perplexity_impl(h, v.D, v.indptr, v.ind, v.data, theta0, rnd, rho_theta_t, out, v.on_device);
+    free_device_csc(h, v.owned);
     return rc;
 }
 
@@ -1633,15 +1898,14 @@ void lda_b200_pcg_fill(lda_b200_pcg *rnd, int64_t count, int64_t n, double *out)
 void lda_b200_pcg_advance(lda_b200_pcg *rnd, uint64_t draws) { advance(rnd, draws); }
 
 // ---- diagnostics -------------------------------------------------------------------------------------------
-int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
-                              const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
-                              double *wc_out, double *n_out) {
-    if (!h) return LDA_B200_EINVAL;
+static int ingest_roundtrip_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                                 const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out, double *wc_out,
+                                 double *n_out, bool src_device) {
     CU(cudaSetDevice(h->device));
     Corpus c;
     double *wc64 = nullptr;
     int rc = dalloc(h, &wc64, (size_t)std::max<int64_t>(D, 1));
-    if (!rc) rc = upload_corpus(h, c, W, D, indptr, ind, data, wc64, true);
+    if (!rc) rc = upload_corpus(h, c, W, D, indptr, ind, data, wc64, true, false, src_device);
     auto back = [&]() -> int {
         if (indptr_out) CU(cudaMemcpyAsync(indptr_out, c.doc_ptr, (size_t)(c.Dl + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
         if (ind_out) CU(cudaMemcpyAsync(ind_out, c.ind, (size_t)c.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
@@ -1657,87 +1921,46 @@ int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const in
     return rc;
 }
 
-// sparse.ToCSC() of a CSR term x document matrix on the device.  The radix sort on the column
-// (document) id is stable, so inside a document the rows stay in ascending order -- exactly what the reference's
-// host-side conversion produces and what fixes the token order of the path.
+int lda_b200_ingest_roundtrip(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
+                              const double *data, int64_t *indptr_out, int32_t *ind_out, float *val_out,
+                              double *wc_out, double *n_out) {
+    if (!h) return LDA_B200_EINVAL;
+    return ingest_roundtrip_impl(h, W, D, indptr, ind, data, indptr_out, ind_out, val_out, wc_out, n_out, false);
+}
+
+int lda_b200_ingest_roundtrip_matrix(lda_b200_handle *h, const lda_b200_matrix *m, int64_t *nnz_out, int64_t *indptr_out,
+                                     int32_t *ind_out, float *val_out, double *wc_out, double *n_out) {
+    if (!h) return LDA_B200_EINVAL;
+    MatrixView v;
+    TRY(open_matrix(h, m, v));
+    int rc = 0;
+    if (nnz_out) *nnz_out = v.indptr ? v.indptr[v.D] : 0;
+    if (indptr_out || ind_out || val_out || wc_out || n_out)
+        rc = ingest_roundtrip_impl(h, v.W, v.D, v.indptr, v.ind, v.data, indptr_out, ind_out, val_out, wc_out, n_out, v.on_device);
+    free_device_csc(h, v.owned);
+    return rc;
+}
+
+// sparse.ToCSC() of a CSR term x document matrix on the device; result copied back to the host
 int lda_b200_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t *row_ptr, const int64_t *col_ind,
                         const double *data, int64_t *indptr_out, int64_t *ind_out, double *data_out) {
     if (!h) return LDA_B200_EINVAL;
-    if (W < 0 || D < 0 || !row_ptr || !indptr_out) return fail(h, LDA_B200_EINVAL, "bad CSR arguments");
-    const int64_t nnz = row_ptr[W] - row_ptr[0];
-    if (row_ptr[0] != 0) return fail(h, LDA_B200_EINVAL, "row_ptr[0] must be 0");
-    for (int64_t r = 0; r < W; ++r)
-        if (row_ptr[r + 1] < row_ptr[r]) return fail(h, LDA_B200_EINVAL, "row_ptr is not non-decreasing at row %lld", (long long)r);
-    if (nnz >= (1LL << 31) || D >= (1LL << 31) || W >= (1LL << 31))
-        return fail(h, LDA_B200_EUNSUPPORTED, "CSR with 2^31 or more entries / rows / columns");
-    if (nnz > 0 && (!col_ind || !data || !ind_out || !data_out)) return fail(h, LDA_B200_EINVAL, "NULL CSR array");
+    if (!indptr_out) return fail(h, LDA_B200_EINVAL, "bad CSR arguments");
     CU(cudaSetDevice(h->device));
-    int64_t *d_rowptr = nullptr, *d_indptr = nullptr, *d_ind64 = nullptr;
-    int32_t *d_cols = nullptr, *d_cols2 = nullptr, *d_rows = nullptr;
-    uint32_t *d_perm = nullptr, *d_perm2 = nullptr;
-    double *d_data = nullptr, *d_data2 = nullptr;
-    void *d_tmp = nullptr;
-    auto run = [&]() -> int {
-        TRY(dalloc(h, &d_rowptr, (size_t)W + 1));
-        TRY(dalloc(h, &d_indptr, (size_t)D + 1));
-        TRY(dalloc(h, &d_cols, (size_t)nnz));
-        TRY(dalloc(h, &d_cols2, (size_t)nnz));
-        TRY(dalloc(h, &d_rows, (size_t)nnz));
-        TRY(dalloc(h, &d_perm, (size_t)nnz));
-        TRY(dalloc(h, &d_perm2, (size_t)nnz));
-        TRY(dalloc(h, &d_data, (size_t)nnz));
-        TRY(dalloc(h, &d_data2, (size_t)nnz));
-        TRY(dalloc(h, &d_ind64, (size_t)nnz));
-        CU(cudaMemcpyAsync(d_rowptr, row_ptr, ((size_t)W + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
-        const int64_t chunk = (int64_t)(h->stage_bytes / 8);
-        for (int64_t p = 0; p < nnz; p += chunk) {
-            const int64_t n = std::min(chunk, nnz - p);
-            TRY(h2d(h, h->stage, col_ind + p, (size_t)n * 8));
-            narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const int64_t *)h->stage, d_cols + p, n, D, h->err_flag);
-            KCHECK();
+    DeviceCSC m;
+    int rc = device_csr_to_csc(h, W, D, row_ptr, col_ind, data, m);
+    auto back = [&]() -> int {
+        if (m.nnz > 0 && (!ind_out || !data_out)) return fail(h, LDA_B200_EINVAL, "NULL CSR array");
+        memcpy(indptr_out, m.h_indptr.data(), ((size_t)D + 1) * sizeof(int64_t));
+        if (m.nnz > 0) {
+            CU(cudaMemcpyAsync(ind_out, m.ind, (size_t)m.nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(data_out, m.data, (size_t)m.nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
-        TRY(h2d(h, d_data, data, (size_t)nnz * sizeof(double)));
-        if (nnz > 0) {
-            csr_expand_rows_kernel<<<grid_for(W * 32, 256, h->sms * 8), 256, 0, h->stream>>>(d_rowptr, W, d_rows);
-            KCHECK();
-            iota_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm, nnz);
-            KCHECK();
-            int bits = 1;
-            while ((1LL << bits) < D) ++bits;
-            size_t tmp_bytes = 0;
-            CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
-            CU(cudaMallocAsync(&d_tmp, tmp_bytes ? tmp_bytes : 1, h->stream));
-            CU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, d_cols, d_cols2, d_perm, d_perm2, (int)nnz, 0, bits, h->stream));
-            h->launches += 4;
-            csc_gather_kernel<<<grid_for(nnz, 256, h->sms * 8), 256, 0, h->stream>>>(d_perm2, d_rows, d_data, nnz, d_ind64, d_data2);
-            KCHECK();
-        }
-        csc_indptr_kernel<<<grid_for(D + 1, 256, h->sms * 8), 256, 0, h->stream>>>(d_cols2, nnz, D, d_indptr);
-        KCHECK();
-        CU(cudaMemcpyAsync(indptr_out, d_indptr, ((size_t)D + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-        if (nnz > 0) {
-            CU(cudaMemcpyAsync(ind_out, d_ind64, (size_t)nnz * sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
-            CU(cudaMemcpyAsync(data_out, d_data2, (size_t)nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        }
-        int bad = 0;
-        CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
-        if (bad) return fail(h, LDA_B200_EINVAL, "a column index lies outside [0, %lld)", (long long)D);
         return 0;
     };
-    const int rc = run();
-    dfree(h, &d_rowptr);
-    dfree(h, &d_indptr);
-    dfree(h, &d_cols);
-    dfree(h, &d_cols2);
-    dfree(h, &d_rows);
-    dfree(h, &d_perm);
-    dfree(h, &d_perm2);
-    dfree(h, &d_data);
-    dfree(h, &d_data2);
-    dfree(h, &d_ind64);
-    if (d_tmp) cudaFreeAsync(d_tmp, h->stream);
+    if (!rc) rc = back();
+    free_device_csc(h, m);
     return rc;
 }
 

@@ -13,6 +13,9 @@ from . import _lib, rand
 
 # term x document matrix in compressed-sparse-column form: what sparse.CSC holds after ToCSC() (lda.go:464-466)
 CSC = namedtuple("CSC", "rows cols indptr ind data")
+# the same matrix in compressed-sparse-row form (sparse.CSR: what the TfidfTransformer emits, weightings.go:79-95):
+# indptr[rows+1], ind = document ids, data
+CSR = namedtuple("CSR", "rows cols indptr ind data")
 
 
 class LearningSchedule:
@@ -56,6 +59,32 @@ def _ptr(a):
     return None if a is None else a.ctypes.data
 
 
+def as_matrix(m, device_convert=True):
+    """lda_b200_matrix descriptor of m in the storage it already has (CSC / CSR / dense), so that ToCSC() and the dense
+    scan run on the GPU; other sparse formats (COO, DOK, ...) and device_convert=False go through as_csc on the host.
+    Returns (descriptor, rows, cols, arrays kept alive for the duration of the call)."""
+    fmt = None
+    if isinstance(m, CSR):
+        fmt, (rows, cols, ptr, ind, data) = _lib.FORMAT_CSR, m
+    elif isinstance(m, CSC):
+        fmt, (rows, cols, ptr, ind, data) = _lib.FORMAT_CSC, m
+    elif device_convert and getattr(m, "format", None) in ("csr", "csc"):
+        fmt = _lib.FORMAT_CSR if m.format == "csr" else _lib.FORMAT_CSC
+        (rows, cols), ptr, ind, data = m.shape, m.indptr, m.indices, m.data
+    elif device_convert and not hasattr(m, "tocsc"):
+        a = np.ascontiguousarray(m, dtype=np.float64)
+        if a.ndim != 2:
+            raise ValueError("nlp: matrix must be 2-dimensional")
+        d = _lib.Matrix(_lib.FORMAT_DENSE, a.shape[0], a.shape[1], None, None, _ptr(a))
+        return d, int(a.shape[0]), int(a.shape[1]), (a,)
+    if fmt is None:
+        fmt, (rows, cols, ptr, ind, data) = _lib.FORMAT_CSC, as_csc(m)
+    ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+    ind = np.ascontiguousarray(ind, dtype=np.int64)
+    data = np.ascontiguousarray(data, dtype=np.float64)
+    return _lib.Matrix(fmt, int(rows), int(cols), _ptr(ptr), _ptr(ind), _ptr(data)), int(rows), int(cols), (ptr, ind, data)
+
+
 class LatentDirichletAllocation:
     """lda.go:68-141.  Use NewLatentDirichletAllocation(k)."""
 
@@ -85,6 +114,7 @@ class LatentDirichletAllocation:
         # --- not in the reference ---
         self.Device = device
         self.DeviceInit = True       # draw the initial nPhi / nTheta from Rnd on the GPU (bit-identical stream)
+        self.DeviceConvert = True    # CSR -> CSC (ToCSC, lda.go:464-466) and the dense scan (utils.go:51-57) on the GPU
         self.PerplexityTrace = []    # perplexities evaluated inside the last fit (lda.go:530-539 hides them)
         self.IterationsRun = 0
         self._h = None
@@ -197,34 +227,33 @@ class LatentDirichletAllocation:
         """lda.go:463-542.  Returns the K x D doc-topic matrix (float64).  nphi0 / ntheta0 (not in the reference)
         replace the RNG draws with an exported init, e.g. the reference's own, for deterministic parity runs; out
         is an optional caller-owned K x D float64 result buffer (e.g. page-locked)."""
-        csc = as_csc(m)
+        desc, rows, cols, _keep = as_matrix(m, self.DeviceConvert)
         h = self._handle()
         L = _lib.lib()
         if not self.DeviceInit:
             if nphi0 is None:
-                nphi0 = self._draws(csc.rows, csc.rows * self.K)
+                nphi0 = self._draws(rows, rows * self.K)
             if ntheta0 is None:
-                ntheta0 = self._draws(csc.cols, csc.cols * self.K)
+                ntheta0 = self._draws(cols, cols * self.K)
         nphi0 = None if nphi0 is None else np.ascontiguousarray(nphi0, dtype=np.float64)
         ntheta0 = None if ntheta0 is None else np.ascontiguousarray(ntheta0, dtype=np.float64)
-        if nphi0 is not None and nphi0.size != csc.rows * self.K:
+        if nphi0 is not None and nphi0.size != rows * self.K:
             raise ValueError("nlp: nphi0 must hold W*K values")
-        if ntheta0 is not None and ntheta0.size != csc.cols * self.K:
+        if ntheta0 is not None and ntheta0.size != cols * self.K:
             raise ValueError("nlp: ntheta0 must hold D*K values")
         theta = None
         if _want_theta:
-            theta = np.zeros((self.K, csc.cols), dtype=np.float64) if out is None else out
-            if theta.shape != (self.K, csc.cols) or theta.dtype != np.float64 or not theta.flags.c_contiguous:
+            theta = np.zeros((self.K, cols), dtype=np.float64) if out is None else out
+            if theta.shape != (self.K, cols) or theta.dtype != np.float64 or not theta.flags.c_contiguous:
                 raise ValueError("nlp: out must be a C-contiguous float64 K x D array")
         cap = self.Iterations // self.PerplexityEvaluationFrequency + 1 if self.PerplexityEvaluationFrequency > 0 else 1
         trace = np.zeros(cap, dtype=np.float64)
         n_evals, iters = C.c_int32(0), C.c_int32(0)
         ctr = self._counters()
-        rc = L.lda_b200_fit(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(nphi0),
-                            _ptr(ntheta0), self.Rnd.src._s, ctr, _ptr(theta), _ptr(trace), cap, C.byref(n_evals),
-                            C.byref(iters))
+        rc = L.lda_b200_fit_matrix(h, desc, _ptr(nphi0), _ptr(ntheta0), self.Rnd.src._s, ctr, _ptr(theta), _ptr(trace), cap,
+                                   C.byref(n_evals), C.byref(iters))
         _lib.check(rc, h)
-        self.w, self.d = csc.rows, csc.cols
+        self.w, self.d = rows, cols
         self._take(ctr)
         self.PerplexityTrace = trace[:n_evals.value].tolist()
         self.IterationsRun = iters.value
@@ -277,19 +306,18 @@ class LatentDirichletAllocation:
         """OnlineTransformer.PartialFit (vectorisers.go:36-39; TODO at lda.go:147): `iterations` SCVB0 iterations over the
         documents of m, continuing from the current model (a fresh random model on first use).  Returns self, or
         the K x D doc-topic matrix of these documents when want_theta is set."""
-        csc = as_csc(m)
+        desc, rows, cols, _keep = as_matrix(m, self.DeviceConvert)
         h = self._handle()
         if ntheta0 is None and not self.DeviceInit:
             if self.IterationsRun == 0 and not self._has_model:
                 raise ValueError("nlp: DeviceInit=False PartialFit needs an existing model")
-            ntheta0 = self._draws(csc.cols, csc.cols * self.K)
+            ntheta0 = self._draws(cols, cols * self.K)
         ntheta0 = None if ntheta0 is None else np.ascontiguousarray(ntheta0, dtype=np.float64)
-        theta = np.zeros((self.K, csc.cols), dtype=np.float64) if want_theta else None
+        theta = np.zeros((self.K, cols), dtype=np.float64) if want_theta else None
         ctr = self._counters()
-        rc = _lib.lib().lda_b200_partial_fit(h, csc.rows, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data),
-                                             _ptr(ntheta0), self.Rnd.src._s, ctr, iterations, _ptr(theta))
+        rc = _lib.lib().lda_b200_partial_fit_matrix(h, desc, _ptr(ntheta0), self.Rnd.src._s, ctr, iterations, _ptr(theta))
         _lib.check(rc, h)
-        self.w, self.d = csc.rows, csc.cols
+        self.w, self.d = rows, cols
         self._take(ctr)
         self._has_model = True
         return theta if want_theta else self
@@ -310,28 +338,27 @@ class LatentDirichletAllocation:
 
     def Transform(self, m, theta0=None, return_passes=False):
         """lda.go:446-453: K x D doc-topic matrix for new documents under the fitted model"""
-        csc = as_csc(m)
+        desc, _rows, cols, _keep = as_matrix(m, self.DeviceConvert)
         h = self._handle()
         if theta0 is None and not self.DeviceInit:
-            theta0 = self._draws(csc.cols, csc.cols * self.K)
+            theta0 = self._draws(cols, cols * self.K)
         theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
-        theta = np.zeros((self.K, csc.cols), dtype=np.float64)
-        passes = np.zeros(csc.cols, dtype=np.int32) if return_passes else None
-        rc = _lib.lib().lda_b200_transform(h, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(theta0),
-                                           self.Rnd.src._s, self.rhoThetaT, _ptr(theta), _ptr(passes))
+        theta = np.zeros((self.K, cols), dtype=np.float64)
+        passes = np.zeros(cols, dtype=np.int32) if return_passes else None
+        rc = _lib.lib().lda_b200_transform_matrix(h, desc, _ptr(theta0), self.Rnd.src._s, self.rhoThetaT, _ptr(theta),
+                                                  _ptr(passes))
         _lib.check(rc, h)
         return (theta, passes) if return_passes else theta
 
     def Perplexity(self, m, theta0=None):
         """lda.go:368-389"""
-        csc = as_csc(m)
+        desc, _rows, cols, _keep = as_matrix(m, self.DeviceConvert)
         h = self._handle()
         if theta0 is None and not self.DeviceInit:
-            theta0 = self._draws(csc.cols, csc.cols * self.K)
+            theta0 = self._draws(cols, cols * self.K)
         theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
         out = C.c_double(0)
-        rc = _lib.lib().lda_b200_perplexity(h, csc.cols, _ptr(csc.indptr), _ptr(csc.ind), _ptr(csc.data), _ptr(theta0),
-                                            self.Rnd.src._s, self.rhoThetaT, C.byref(out))
+        rc = _lib.lib().lda_b200_perplexity_matrix(h, desc, _ptr(theta0), self.Rnd.src._s, self.rhoThetaT, C.byref(out))
         _lib.check(rc, h)
         return out.value
 

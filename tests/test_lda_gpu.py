@@ -13,7 +13,7 @@ import pytest
 import corpus_synth
 import nlp_b200
 from nlp_b200 import _lib, rand
-from nlp_b200.lda import CSC, as_csc
+from nlp_b200.lda import CSC, CSR, as_csc, as_matrix
 from oracle import oracle as O
 from tests.fixtures import EXPECTED_DOCS, FIT_CASES, FIXTURE_A, FIXTURE_B
 
@@ -341,6 +341,101 @@ def test_ingest_roundtrip_bit_exact():
     assert np.array_equal(val.astype(np.float64), m.data)  # integer counts are exact in fp32
     assert np.array_equal(wc, np.add.reduceat(m.data, m.indptr[:-1]))  # lda.go:476-480
     assert n.value == m.data.sum()                                     # lda.go:481
+
+
+def _device_view(lda, m):
+    """(indptr, ind, val, wc, N) the device holds for matrix m after the *_matrix ingestion (CSC / CSR / dense)"""
+    import ctypes as C
+    desc, rows, cols, _keep = as_matrix(m)
+    h = lda._handle()
+    nnz = C.c_int64(0)
+    L = _lib.lib()
+    _lib.check(L.lda_b200_ingest_roundtrip_matrix(h, desc, C.byref(nnz), None, None, None, None, None), h)
+    indptr = np.zeros(cols + 1, dtype=np.int64)
+    ind = np.zeros(nnz.value, dtype=np.int32)
+    val = np.zeros(nnz.value, dtype=np.float32)
+    wc = np.zeros(cols, dtype=np.float64)
+    n = C.c_double(0)
+    _lib.check(L.lda_b200_ingest_roundtrip_matrix(h, desc, None, indptr.ctypes.data, ind.ctypes.data, val.ctypes.data,
+                                                  wc.ctypes.data, C.byref(n)), h)
+    return indptr, ind, val, wc, n.value
+
+
+def test_matrix_ingestion_bit_exact():
+    """CSR (sparse.ToCSC, lda.go:464-466) and dense (utils.go:51-57) inputs converted on the device give exactly the
+    token stream the host-side conversion gives: same indptr, word ids, values, wc (lda.go:476-480) and N (:481)."""
+    import scipy.sparse as sp
+    lda = new_lda(3)
+    rng = np.random.default_rng(11)
+    for (W, D, dens) in [(40, 33, 0.2), (500, 260, 0.03), (9, 2000, 0.3), (200, 1, 0.5), (1, 50, 0.6), (30, 30, 0.0)]:
+        a = sp.random(W, D, density=dens, format="csr", random_state=rng, data_rvs=lambda n: rng.integers(1, 9, n).astype(float))
+        want = as_csc(a)
+        wc = np.zeros(D)
+        np.add.at(wc, np.repeat(np.arange(D), np.diff(want.indptr)), want.data)
+        dense = a.toarray()
+        dense[dense == 0] = 0.0
+        if W > 2 and D > 2:
+            dense[1, 2] = -0.0   # Go's `v != 0` skips a negative zero as well
+            a = sp.csr_matrix(dense)
+            want = as_csc(a)
+            wc = np.zeros(D)
+            np.add.at(wc, np.repeat(np.arange(D), np.diff(want.indptr)), want.data)
+        for m in (a, CSR(W, D, a.indptr, a.indices, a.data), dense, want, sp.csc_matrix(a)):
+            indptr, ind, val, wc_d, n = _device_view(lda, m)
+            assert np.array_equal(indptr, want.indptr), type(m)
+            assert np.array_equal(ind.astype(np.int64), want.ind), type(m)
+            assert np.array_equal(val.astype(np.float64), want.data), type(m)
+            assert np.array_equal(wc_d, wc) and n == want.data.sum(), type(m)
+    # CSR rows whose document ids are not sorted: words still come out ascending inside a document
+    a = sp.random(60, 45, density=0.2, format="csr", random_state=rng, data_rvs=lambda n: rng.integers(1, 5, n).astype(float))
+    ptr, ci, dv = a.indptr.copy(), a.indices.copy(), a.data.copy()
+    for r in range(60):
+        q = rng.permutation(ptr[r + 1] - ptr[r])
+        ci[ptr[r]:ptr[r + 1]], dv[ptr[r]:ptr[r + 1]] = ci[ptr[r]:ptr[r + 1]][q], dv[ptr[r]:ptr[r + 1]][q]
+    want = as_csc(a)
+    indptr, ind, val, _, _ = _device_view(lda, CSR(60, 45, ptr, ci, dv))
+    assert np.array_equal(indptr, want.indptr) and np.array_equal(ind, want.ind) and np.array_equal(val, want.data)
+
+
+def test_matrix_inputs_through_every_call():
+    """Fit / Transform / Perplexity / PartialFit give the same results whether the conversion to CSC ran on the device
+    (CSR, dense) or on the host, and they match the oracle."""
+    import scipy.sparse as sp
+    m = synth(150, 400, 30)
+    csc = sp.csc_matrix((m.data, m.ind, m.indptr), shape=(m.rows, m.cols))
+    f = dict(Iterations=4, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, BatchSize=64)
+    base, o = run_pair(m, 7, 4, BatchSize=64)
+    th0 = new_lda(7, **f).FitTransform(m)
+    t0, p0 = base.Transform(m), base.Perplexity(m)
+    for x in (csc.tocsr(), csc.toarray(), CSR(m.rows, m.cols, *[getattr(csc.tocsr(), a) for a in ("indptr", "indices", "data")])):
+        lda = new_lda(7, **f)
+        th = lda.FitTransform(x)
+        assert np.abs(th - th0).max() <= 1e-4
+        np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+        np.testing.assert_allclose(lda.PerplexityTrace, base.PerplexityTrace, rtol=1e-5)
+        # same model, same initial theta: the device holds the same token stream, so Transform is identical
+        base.Rnd = rand.New(rand.NewSource(5))
+        tx = base.Transform(x)
+        base.Rnd = rand.New(rand.NewSource(5))
+        assert np.array_equal(tx, base.Transform(m))
+        base.Rnd = rand.New(rand.NewSource(5))
+        px = base.Perplexity(x)
+        base.Rnd = rand.New(rand.NewSource(5))
+        np.testing.assert_allclose(px, base.Perplexity(m), rtol=1e-12)
+        host = new_lda(7, DeviceConvert=False, **f)
+        host.FitTransform(x)
+        np.testing.assert_allclose(host.PerplexityTrace, lda.PerplexityTrace, rtol=1e-5)
+    assert np.isfinite(t0).all() and np.isfinite(p0)
+    pf = new_lda(7, BatchSize=64)
+    pf.PartialFit(csc.tocsr(), iterations=2)
+    pf2 = new_lda(7, BatchSize=64)
+    pf2.PartialFit(m, iterations=2)
+    np.testing.assert_allclose(pf.GetState()[1], pf2.GetState()[1], rtol=1e-5)
+    # a matrix with the wrong number of rows is rejected instead of indexing outside nPhi
+    with pytest.raises(_lib.LdaB200Error, match="rows"):
+        base.Transform(np.ones((m.rows + 1, 3)))
+    with pytest.raises(_lib.LdaB200Error, match="rows"):
+        base.Perplexity(sp.csr_matrix(np.ones((m.rows - 1, 3))))
 
 
 def test_device_csr_to_csc_bit_exact():
