@@ -112,7 +112,7 @@ class LatentDirichletAllocation {
     template <class M>
     LatentDirichletAllocation &Fit(const M &m) {
         std::string err;
-        fit(toCSC(m), false, nullptr, err);
+        fit(describe(m), false, nullptr, err);
         if (!err.empty()) throw std::runtime_error(err);
         return *this;
     }
@@ -120,19 +120,18 @@ class LatentDirichletAllocation {
     template <class M>
     bool FitTransform(const M &m, mat::Dense &theta, std::string *err = nullptr) {
         std::string e;
-        fit(toCSC(m), true, &theta, e);
+        fit(describe(m), true, &theta, e);
         if (err) *err = e;
         return e.empty();
     }
     // lda.go:446-453
     template <class M>
     bool Transform(const M &m, mat::Dense &theta, std::string *err = nullptr) {
-        const sparse::CSC c = toCSC(m);
+        const lda_b200_matrix c = describe(m);
         std::string e;
         if (handle(e)) {
             std::vector<double> out((size_t)K * c.cols);
-            if (lda_b200_transform(h_, c.cols, c.indptr.data(), ptr(c.ind), ptr(c.data), nullptr, &Rnd.src.s, rhoThetaT_,
-                                   out.data(), nullptr))
+            if (lda_b200_transform_matrix(h_, &c, nullptr, &Rnd.src.s, rhoThetaT_, out.data(), nullptr))
                 e = std::string("nlp: ") + lda_b200_last_error(h_);
             else
                 theta = mat::NewDense(K, (int)c.cols, std::move(out));
@@ -143,11 +142,10 @@ class LatentDirichletAllocation {
     // lda.go:368-389
     template <class M>
     double Perplexity(const M &m) {
-        const sparse::CSC c = toCSC(m);
+        const lda_b200_matrix c = describe(m);
         std::string e;
         double out = 0;
-        if (handle(e) && lda_b200_perplexity(h_, c.cols, c.indptr.data(), ptr(c.ind), ptr(c.data), nullptr, &Rnd.src.s,
-                                             rhoThetaT_, &out))
+        if (handle(e) && lda_b200_perplexity_matrix(h_, &c, nullptr, &Rnd.src.s, rhoThetaT_, &out))
             e = std::string("nlp: ") + lda_b200_last_error(h_);
         if (!e.empty()) throw std::runtime_error(e);
         return out;
@@ -163,26 +161,19 @@ class LatentDirichletAllocation {
         return mat::NewDense(K, (int)W, std::move(out));
     }
 
-    // ColNonZeroElemDo's dense branch (utils.go:51-57): rows ascending, exact zeros skipped
-    static sparse::CSC toCSC(const mat::Dense &m) {
-        sparse::CSC c;
-        c.rows = m.r, c.cols = m.c;
-        c.indptr.assign((size_t)m.c + 1, 0);
-        for (int j = 0; j < m.c; ++j) {
-            for (int i = 0; i < m.r; ++i) {
-                const double v = m.At(i, j);
-                if (v != 0) {
-                    c.ind.push_back(i);
-                    c.data.push_back(v);
-                }
-            }
-            c.indptr[(size_t)j + 1] = (int64_t)c.ind.size();
-        }
-        return c;
+    // The matrix in the storage it already has (lda_b200_matrix): sparse.ToCSC() (lda.go:464-466) and the dense scan of
+    // ColNonZeroElemDo (utils.go:51-57: rows ascending, exact zeros skipped) run on the device.
+    static lda_b200_matrix describe(const mat::Dense &m) {
+        return lda_b200_matrix{LDA_B200_DENSE, m.r, m.c, nullptr, nullptr, ptr(m.data)};
     }
-    static const sparse::CSC &toCSC(const sparse::CSC &m) { return m; }
-    // sparse.CSR.ToCSC() (lda.go:464-466), on the device
-    sparse::CSC toCSC(const sparse::CSR &m) {
+    static lda_b200_matrix describe(const sparse::CSC &m) {
+        return lda_b200_matrix{LDA_B200_CSC, m.rows, m.cols, ptr(m.indptr), ptr(m.ind), ptr(m.data)};
+    }
+    static lda_b200_matrix describe(const sparse::CSR &m) {
+        return lda_b200_matrix{LDA_B200_CSR, m.rows, m.cols, ptr(m.indptr), ptr(m.ind), ptr(m.data)};
+    }
+    // sparse.CSR.ToCSC() (lda.go:464-466) on the device, result back on the host
+    sparse::CSC ToCSC(const sparse::CSR &m) {
         std::string e;
         if (!handle(e)) throw std::runtime_error(e);
         sparse::CSC c;
@@ -231,14 +222,14 @@ class LatentDirichletAllocation {
         }
         return true;
     }
-    void fit(const sparse::CSC &c, bool want, mat::Dense *theta, std::string &err) {
+    void fit(const lda_b200_matrix &c, bool want, mat::Dense *theta, std::string &err) {
         if (!handle(err)) return;
         std::vector<double> out(want ? (size_t)K * c.cols : 0);
         std::vector<double> trace(PerplexityEvaluationFrequency > 0 ? (size_t)Iterations / PerplexityEvaluationFrequency + 1 : 1);
         lda_b200_counters ctr{rhoPhiT_, rhoThetaT_, wordsInCorpus_};
         int32_t n_evals = 0, iters = 0;
-        if (lda_b200_fit(h_, c.rows, c.cols, c.indptr.data(), ptr(c.ind), ptr(c.data), nullptr, nullptr, &Rnd.src.s, &ctr,
-                         want ? out.data() : nullptr, trace.data(), (int32_t)trace.size(), &n_evals, &iters)) {
+        if (lda_b200_fit_matrix(h_, &c, nullptr, nullptr, &Rnd.src.s, &ctr, want ? out.data() : nullptr, trace.data(),
+                                (int32_t)trace.size(), &n_evals, &iters)) {
             err = std::string("nlp: ") + lda_b200_last_error(h_);
             return;
         }

@@ -85,6 +85,18 @@ SYMBOLS = {
     "lda_b200_last_allreduce_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
+# every symbol include/lda_b200_index.h declares
+SYMBOLS.update({
+    "lda_b200_index_create": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "lda_b200_index_destroy": (None, [_P]),
+    "lda_b200_index_last_error": (C.c_char_p, [_P]),
+    "lda_b200_index_add": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
+    "lda_b200_index_remove": (C.c_int, [_P, C.c_int64]),
+    "lda_b200_index_len": (C.c_int64, [_P]),
+    "lda_b200_index_search": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
+    "lda_b200_index_last_search_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+})
+
 _LIB = None
 
 
@@ -113,4 +125,10 @@ def lib():
 def check(code, handle=None):
     if code != 0:
         text = lib().lda_b200_last_error(handle)
+        raise LdaB200Error(code, text.decode() if text else "")
+
+
+def check_index(code, index=None):
+    if code != 0:
+        text = lib().lda_b200_index_last_error(index)
         raise LdaB200Error(code, text.decode() if text else "")

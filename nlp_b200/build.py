@@ -4,9 +4,9 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "csrc", "lda_b200.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "pcg.cuh", "nccl_dl.h")] + [
-    os.path.join(HERE, "..", "include", "lda_b200.h")]
+SRCS = [os.path.join(HERE, "csrc", f) for f in ("lda_b200.cu", "index_b200.cu")]
+DEPS = SRCS + [os.path.join(HERE, "csrc", f) for f in ("kernels.cuh", "pcg.cuh", "nccl_dl.h", "index_kernels.cuh")] + [
+    os.path.join(HERE, "..", "include", f) for f in ("lda_b200.h", "lda_b200_index.h")]
 OUT = os.path.join(HERE, "liblda_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
@@ -26,7 +26,7 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC, "-ldl"]
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT] + SRCS + ["-ldl"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or r.returncode:
         sys.stderr.write(r.stdout + r.stderr)

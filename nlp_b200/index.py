@@ -1,0 +1,142 @@
+"""Host-side mirror of `nlp.LinearScanIndex` (reference index.go:60-135) over the C ABI of liblda_b200.so
+(include/lda_b200_index.h): exact nearest-neighbour search over document vectors -- e.g. the K x D doc-topic matrix of
+the LDA path -- by a linear scan on the GPU.  Same method names, argument meaning and result type (`Match`) as the Go
+type; `IndexColumns` / `SearchColumns` are the batched forms (`ColDo(m, index.Index)`, many queries per scan).  All
+arithmetic runs in CUDA kernels; this file only marshals arguments and maps arbitrary Python ids to int64 handles."""
+import ctypes as C
+from collections import namedtuple
+
+import numpy as np
+
+from . import _lib
+from .measures import pairwise
+
+Match = namedtuple("Match", "Distance ID")   # index.go:13-19
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data
+
+
+class LinearScanIndex:
+    """index.go:60-135.  Use NewLinearScanIndex(compareFN)."""
+
+    def __init__(self, compareFN, device=0):
+        if not isinstance(compareFN, pairwise.Comparer):
+            raise TypeError("nlp: compareFN must be one of nlp_b200.measures.pairwise (the kernels are specialised on it)")
+        self.distance = compareFN
+        self._ids = {}        # int64 handle -> caller's id (index.go:16: ID interface{})
+        self._handles = {}    # caller's id -> handles in insertion order (Remove drops the first, index.go:121-122)
+        self._next = 0
+        self._dim = None      # fixed by the first vector
+        h = C.c_void_p()
+        _lib.check_index(_lib.lib().lda_b200_index_create(device, compareFN.code, C.byref(h)))
+        self._h = h
+
+    def Close(self):
+        if getattr(self, "_h", None) is not None:
+            _lib.lib().lda_b200_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.Close()
+        except Exception:
+            pass
+
+    def __len__(self):
+        return int(_lib.lib().lda_b200_index_len(self._h))
+
+    def _new_handles(self, ids):
+        out = np.arange(self._next, self._next + len(ids), dtype=np.int64)
+        self._next += len(ids)
+        return out
+
+    def _register(self, handles, ids):
+        for hd, id in zip(handles.tolist(), ids):
+            self._ids[hd] = id
+            self._handles.setdefault(id, []).append(hd)
+
+    # ---- reference API -----------------------------------------------------------------------------------
+    def Index(self, v, id):
+        """index.go:79-84"""
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
+        handles = self._new_handles([id])
+        _lib.check_index(_lib.lib().lda_b200_index_add(self._h, v.size, 1, _ptr(v), 1, _ptr(handles)), self._h)
+        self._dim = v.size
+        self._register(handles, [id])
+
+    def Search(self, qv, k):
+        """index.go:85-115: up to k Matches, nearest first (the reference returns the same matches in heap order)"""
+        qv = np.ascontiguousarray(np.asarray(qv, dtype=np.float64).ravel())
+        return self.SearchColumns(qv.reshape(-1, 1), k)[0]
+
+    def Remove(self, id):
+        """index.go:117-135"""
+        hs = self._handles.get(id)
+        if not hs:
+            return
+        hd = hs.pop(0)
+        if not hs:
+            del self._handles[id]
+        del self._ids[hd]
+        _lib.check_index(_lib.lib().lda_b200_index_remove(self._h, hd), self._h)
+
+    # ---- batched forms -------------------------------------------------------------------------------------
+    def IndexColumns(self, m, ids=None):
+        """ColDo(m, func(j, v) { index.Index(v, ids[j]) }): every column of the dim x n matrix m (e.g. the K x D matrix
+        Transform returns), ids default to the column numbers continuing from the current size"""
+        m = np.asarray(m, dtype=np.float64)
+        if m.ndim != 2:
+            raise ValueError("nlp: matrix must be 2-dimensional")
+        if not m.flags.c_contiguous:
+            m = np.ascontiguousarray(m)
+        n = m.shape[1]
+        if ids is None:
+            base = len(self)
+            ids = list(range(base, base + n))
+        if len(ids) != n:
+            raise ValueError("nlp: one id per column")
+        handles = self._new_handles(ids)
+        _lib.check_index(_lib.lib().lda_b200_index_add(self._h, m.shape[0], n, _ptr(m), max(n, 1), _ptr(handles)), self._h)
+        if n:
+            self._dim = m.shape[0]
+        self._register(handles, ids)
+
+    def SearchColumns(self, q, k):
+        """Search for every column of the dim x nq matrix q in one pass over the index -> list of Match lists"""
+        ids, dist, found = self.SearchRaw(q, k)
+        out = []
+        for i in range(ids.shape[0]):
+            out.append([Match(float(dist[i, r]), self._ids[int(ids[i, r])]) for r in range(int(found[i]))])
+        return out
+
+    def SearchRaw(self, q, k):
+        """as SearchColumns, returning (handles int64[nq,k], distances float64[nq,k], found int32[nq]) arrays; handles are
+        the positions-at-insertion numbers unless ids were given"""
+        q = np.asarray(q, dtype=np.float64)
+        if q.ndim != 2:
+            raise ValueError("nlp: queries must be the columns of a 2-dimensional matrix")
+        if not q.flags.c_contiguous:
+            q = np.ascontiguousarray(q)
+        nq = q.shape[1]
+        k = int(k)
+        ids = np.zeros((nq, max(k, 1)), dtype=np.int64)
+        dist = np.zeros((nq, max(k, 1)), dtype=np.float64)
+        found = np.zeros(nq, dtype=np.int32)
+        if self._dim is not None and q.shape[0] != self._dim:
+            raise ValueError("nlp: query has %d elements, the index holds vectors of %d" % (q.shape[0], self._dim))
+        _lib.check_index(_lib.lib().lda_b200_index_search(self._h, nq, _ptr(q), max(nq, 1), k, _ptr(ids), _ptr(dist),
+                                                           _ptr(found)), self._h)
+        return ids, dist, found
+
+    def LastSearchTime(self):
+        """(scan ms, select ms, kernel launches) of the last search, CUDA events on the index's stream"""
+        a, b, n = C.c_float(0), C.c_float(0), C.c_int32(0)
+        _lib.lib().lda_b200_index_last_search_time(self._h, C.byref(a), C.byref(b), C.byref(n))
+        return a.value, b.value, n.value
+
+
+def NewLinearScanIndex(compareFN, device=0):
+    """index.go:74-76"""
+    return LinearScanIndex(compareFN, device=device)

@@ -99,7 +99,8 @@ static void TestLDATransform() {
     }
 }
 
-// not in the reference: the sparse branch (lda.go:464-466) through CSR -> ToCSC on the device must equal the dense branch
+// not in the reference: the sparse branch (lda.go:464-466) -- a CSR handed over as it is, and its device-side ToCSC()
+// read back to the host first -- must equal the dense branch
 static void TestSparseInput() {
     nlp::mat::Dense in = nlp::mat::NewDense(9, 9, dataB);
     nlp::sparse::CSR csr;
@@ -113,16 +114,18 @@ static void TestSparseInput() {
             }
         csr.indptr.push_back((int64_t)csr.ind.size());
     }
-    nlp::mat::Dense a, b;
-    for (int pass = 0; pass < 2; ++pass) {
+    nlp::mat::Dense a, b, c;
+    for (int pass = 0; pass < 3; ++pass) {
         std::unique_ptr<nlp::LatentDirichletAllocation> lda(nlp::NewLatentDirichletAllocation(3));
         lda->Rnd = nlp::rand::New(nlp::rand::NewSource(0));
         lda->Iterations = 10;
         std::string err;
-        bool ok = pass == 0 ? lda->FitTransform(in, a, &err) : lda->FitTransform(lda->toCSC(csr), b, &err);
+        bool ok = pass == 0   ? lda->FitTransform(in, a, &err)
+                  : pass == 1 ? lda->FitTransform(csr, b, &err)
+                              : lda->FitTransform(lda->ToCSC(csr), c, &err);
         if (!ok) Errorf("%s\n", err.c_str());
     }
-    if (!nlp::mat::EqualApprox(a, b, 0)) Errorf("sparse and dense inputs disagree\n");
+    if (!nlp::mat::EqualApprox(a, b, 0) || !nlp::mat::EqualApprox(a, c, 0)) Errorf("sparse and dense inputs disagree\n");
 }
 
 int main() {

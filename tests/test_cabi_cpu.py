@@ -16,10 +16,16 @@ from tests.fixtures import FIXTURE_A, FIXTURE_B
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+HEADERS = ("lda_b200.h", "lda_b200_index.h")
+
+
 def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "lda_b200.h")).read()
-    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\b(lda_b200_[a-z0-9_]+)\s*\(", text)))
+    names = set()
+    for header in HEADERS:
+        text = open(os.path.join(ROOT, "include", header)).read()
+        text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        names |= set(re.findall(r"\b(lda_b200_[a-z0-9_]+)\s*\(", text))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -33,10 +39,11 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_no_torch_types_in_the_abi():
-    text = open(os.path.join(ROOT, "include", "lda_b200.h")).read()
-    assert 'extern "C"' in text
-    code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    assert "torch" not in code and "at::" not in code and "std::" not in code and "Tensor" not in code
+    for header in HEADERS:
+        text = open(os.path.join(ROOT, "include", header)).read()
+        assert 'extern "C"' in text
+        code = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+        assert "torch" not in code and "at::" not in code and "std::" not in code and "Tensor" not in code
 
 
 def test_default_config_matches_reference_defaults():
@@ -157,6 +164,8 @@ def test_product_fails_loudly_without_gpu():
         lda.Fit(FIXTURE_A)
     with pytest.raises(_lib.LdaB200Error):
         lda.Transform(FIXTURE_A)
+    with pytest.raises(_lib.LdaB200Error, match="no CPU fallback"):
+        nlp_b200.NewLinearScanIndex(nlp_b200.pairwise.CosineDistance)
 
 
 def test_product_does_not_import_the_oracle():
@@ -164,7 +173,7 @@ def test_product_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
-                for bad in ("import oracle", "from oracle", "liblda_oracle", "oracle/"):
+                for bad in ("import oracle", "from oracle", "liblda_oracle", "libindex_oracle", "oracle/"):
                     assert bad not in text, (os.path.join(dirpath, f), bad)
 
 
