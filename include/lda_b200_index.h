@@ -63,8 +63,10 @@ int lda_b200_index_search(lda_b200_index *ix, int64_t nq, const double *q, int64
                           double *dist_out, int32_t *found_out);
 
 /* device time (ms, CUDA events on the index's stream) the last lda_b200_index_search spent in the distance scan and in
- * the top-k selection, and the number of kernels it launched (tools/bench_search.py) */
-int lda_b200_index_last_search_time(const lda_b200_index *ix, float *scan_ms, float *select_ms, int32_t *launches);
+ * the top-k selection, the number of kernels it launched and how many times the scan read the whole index (one pass
+ * serves up to 64 queries under the dot-product comparers, else up to 16) -- tools/bench_search.py */
+int lda_b200_index_last_search_time(const lda_b200_index *ix, float *scan_ms, float *select_ms, int32_t *launches,
+                                    int32_t *passes);
 
 #ifdef __cplusplus
 }

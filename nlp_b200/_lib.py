@@ -94,7 +94,8 @@ SYMBOLS.update({
     "lda_b200_index_remove": (C.c_int, [_P, C.c_int64]),
     "lda_b200_index_len": (C.c_int64, [_P]),
     "lda_b200_index_search": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),
-    "lda_b200_index_last_search_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "lda_b200_index_last_search_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int32),
+                                                  C.POINTER(C.c_int32)]),
 })
 
 _LIB = None

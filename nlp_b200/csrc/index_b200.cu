@@ -6,10 +6,12 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/lda_b200.h"
@@ -33,13 +35,13 @@ struct lda_b200_index {
     int dim = 0;
     int64_t n = 0, cap = 0;
     double *vec = nullptr;   // [dim][cap]
-    double *norm = nullptr;  // [cap]
+    double *norm = nullptr;  // [cap] reciprocal Euclidean norms
     int64_t *ids = nullptr;  // [cap]
     std::vector<int64_t> h_ids;
 
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float scan_ms = 0, select_ms = 0;
-    int launches = 0;
+    int launches = 0, passes = 0;
 };
 
 namespace {
@@ -94,7 +96,8 @@ inline int grid_for(int64_t n, int threads, int cap) {
 // room for `extra` more vectors: capacity doubles, the rows of the [dim][cap] matrix move to their new pitch
 int reserve(lda_b200_index *ix, int64_t extra) {
     if (ix->n + extra <= ix->cap) return 0;
-    const int64_t ncap = std::max<int64_t>({ix->cap * 2, ix->n + extra, 1024});
+    // a multiple of the bulk-copy tile: the copy of a whole tile of any row stays inside the row
+    const int64_t ncap = (std::max<int64_t>({ix->cap * 2, ix->n + extra, 1024}) + MMA_TV - 1) / MMA_TV * MMA_TV;
     double *nvec = nullptr, *nnorm = nullptr;
     int64_t *nids = nullptr;
     ITRY(ialloc(ix, &nvec, (size_t)ix->dim * ncap));
@@ -116,33 +119,64 @@ int reserve(lda_b200_index *ix, int64_t extra) {
     return 0;
 }
 
-template <int QB>
-int launch_scan(lda_b200_index *ix, const ScanArgs &a, int nchunks) {
+// queries per pass over the index and the kernel that runs it
+struct ScanPlan {
+    int QB;
+    bool mma;  // FP64 tensor-core kernel (dot-product comparers, dim % 4 == 0, more than 4 queries)
+};
+ScanPlan plan_scan(const lda_b200_index *ix, int nb) {
+    if (nb == 1) return {1, false};
+    if (nb <= 4) return {4, false};
+    const bool dot = acc_class(ix->comparer) == ACC_DOT && ix->dim % 4 == 0 && !getenv("LDA_B200_INDEX_NO_MMA");
+    const size_t limit = (size_t)227 * 1024;
+    if (dot && nb > 16 && scan_mma_smem_bytes(ix->dim, 64) <= limit) return {64, true};
+    if (dot && scan_mma_smem_bytes(ix->dim, 16) <= limit) return {16, true};
+    return {16, false};
+}
+
+int launch_scan(lda_b200_index *ix, const ScanArgs &a, const ScanPlan &pl, int nchunks) {
+    if (pl.mma) {
+        const size_t smem = scan_mma_smem_bytes(a.dim, pl.QB);
+        const dim3 grid((unsigned)grid_for(a.n, MMA_TV, ix->sms), (unsigned)nchunks);
+        auto go = [&](auto kern) -> int {
+            ICU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 256, smem, ix->stream>>>(a);
+            IKCHECK();
+            return 0;
+        };
+        return pl.QB == 64 ? go(index_scan_mma_kernel<8>) : go(index_scan_mma_kernel<2>);
+    }
     const dim3 grid((unsigned)grid_for(a.n, 256, ix->sms * 6), (unsigned)nchunks);
-    const size_t smem = (size_t)a.ktile * QB * sizeof(double);
+    const size_t smem = (size_t)a.ktile * pl.QB * sizeof(double);
+    auto by_qb = [&](auto cls_tag) -> int {
+        constexpr int C = decltype(cls_tag)::value;
+        if (pl.QB == 1)
+            index_scan_kernel<1, C><<<grid, 256, smem, ix->stream>>>(a);
+        else if (pl.QB == 4)
+            index_scan_kernel<4, C><<<grid, 256, smem, ix->stream>>>(a);
+        else
+            index_scan_kernel<16, C><<<grid, 256, smem, ix->stream>>>(a);
+        IKCHECK();
+        return 0;
+    };
     switch (acc_class(a.comparer)) {
         case ACC_DOT:
-            index_scan_kernel<QB, ACC_DOT><<<grid, 256, smem, ix->stream>>>(a);
-            break;
+            return by_qb(std::integral_constant<int, ACC_DOT>{});
         case ACC_L2:
-            index_scan_kernel<QB, ACC_L2><<<grid, 256, smem, ix->stream>>>(a);
-            break;
+            return by_qb(std::integral_constant<int, ACC_L2>{});
         case ACC_L1:
-            index_scan_kernel<QB, ACC_L1><<<grid, 256, smem, ix->stream>>>(a);
-            break;
+            return by_qb(std::integral_constant<int, ACC_L1>{});
         default:
-            index_scan_kernel<QB, ACC_HAMMING><<<grid, 256, smem, ix->stream>>>(a);
-            break;
+            return by_qb(std::integral_constant<int, ACC_HAMMING>{});
     }
-    IKCHECK();
-    return 0;
 }
 
 // Search for one batch of nb queries already on the device as a dim x nb row-major matrix
 int search_batch(lda_b200_index *ix, const double *d_q, int nb, int k, int64_t *ids_out, double *dist_out, int32_t *found_out) {
     const int64_t n = ix->n;
     const int k_eff = (int)std::min<int64_t>(k, n);
-    const int QB = nb == 1 ? 1 : nb <= 4 ? 4 : 16;
+    const ScanPlan pl = plan_scan(ix, nb);
+    const int QB = pl.QB;
     const int nchunks = (nb + QB - 1) / QB;
     int P = 1;
     while (P < std::max(k_eff, 1)) P <<= 1;
@@ -173,9 +207,9 @@ int search_batch(lda_b200_index *ix, const double *d_q, int nb, int k, int64_t *
         IKCHECK();
         ScanArgs a;
         a.vec = ix->vec;
-        a.norm = ix->norm;
+        a.inorm = ix->norm;
         a.qpack = qpack;
-        a.qnorm = qnorm;
+        a.qinorm = qnorm;
         a.keys = keys;
         a.cap = ix->cap;
         a.n = n;
@@ -183,14 +217,8 @@ int search_batch(lda_b200_index *ix, const double *d_q, int nb, int k, int64_t *
         a.nq = nb;
         a.comparer = ix->comparer;
         a.ktile = std::min(ix->dim, 4096 / QB);  // <= 32 KB of shared memory
-        if (n > 0) {
-            if (QB == 1)
-                ITRY(launch_scan<1>(ix, a, nchunks));
-            else if (QB == 4)
-                ITRY(launch_scan<4>(ix, a, nchunks));
-            else
-                ITRY(launch_scan<16>(ix, a, nchunks));
-        }
+        if (n > 0) ITRY(launch_scan(ix, a, pl, nchunks));
+        ix->passes += nchunks;
         ICU(cudaEventRecord(ix->ev[1], ix->stream));
 
         // ---- the k smallest (index.go:99-112 keeps them in a heap; here: radix selection of the k-th composite) ----
@@ -357,7 +385,7 @@ int lda_b200_index_search(lda_b200_index *ix, int64_t nq, const double *q, int64
     if (nq < 0 || (nq > 0 && (!q || !ids_out || !dist_out)) || ldq < 1 || (nq > 1 && ldq < nq))
         return ifail(ix, LDA_B200_EINVAL, "bad query batch (nq = %lld, ldq = %lld)", (long long)nq, (long long)ldq);
     ix->scan_ms = ix->select_ms = 0;
-    ix->launches = 0;
+    ix->launches = ix->passes = 0;
     if (nq == 0) return 0;
     if (ix->n == 0) {  // index.go:101-103: fewer than k vectors -> what there is
         for (int64_t i = 0; i < nq * k; ++i) {
@@ -388,11 +416,13 @@ int lda_b200_index_search(lda_b200_index *ix, int64_t nq, const double *q, int64
     return rc;
 }
 
-int lda_b200_index_last_search_time(const lda_b200_index *ix, float *scan_ms, float *select_ms, int32_t *launches) {
+int lda_b200_index_last_search_time(const lda_b200_index *ix, float *scan_ms, float *select_ms, int32_t *launches,
+                                    int32_t *passes) {
     if (!ix) return LDA_B200_EINVAL;
     if (scan_ms) *scan_ms = ix->scan_ms;
     if (select_ms) *select_ms = ix->select_ms;
     if (launches) *launches = ix->launches;
+    if (passes) *passes = ix->passes;
     return 0;
 }
 

@@ -5,7 +5,8 @@
 //   vec   [dim][cap]   vector j is column j -- the K x D doc-topic matrix Transform / FitTransform return is indexed as
 //                      it is (ColDo(theta, index.Index)); a thread owns one vector, so every load of a warp is one
 //                      contiguous 256-byte segment of a row
-//   norm  [cap]        Euclidean norm of every indexed vector (sparse.Norm(v, 2), comparisons.go:21-22)
+//   inorm [cap]        1 / Euclidean norm of every indexed vector (sparse.Norm(v, 2), comparisons.go:21-22); +Inf for an
+//                      all-zero vector, which turns its cosine into 0 * Inf = NaN exactly where the reference returns NaN
 //   keys  [nq][n]      order-preserving 64-bit image of distance(query q, vector j)
 // The scan is HBM-bound: dim * 8 bytes per (vector, batch of QB queries); nothing here is a dense contraction worth a
 // tensor core at the batch sizes a search has.
@@ -50,22 +51,22 @@ __device__ __forceinline__ double key_to_dist(uint64_t k) {
     return __longlong_as_double((long long)b);
 }
 
-// Euclidean norm of the vectors [j0, j0+n) (sum of squares in index order, like the oracle)
-__global__ void __launch_bounds__(256) index_norms_kernel(const double *vec, int64_t cap, int dim, int64_t j0, int64_t n, double *norm) {
+// 1 / Euclidean norm of the vectors [j0, j0+n) (sum of squares in index order, like the oracle)
+__global__ void __launch_bounds__(256) index_norms_kernel(const double *vec, int64_t cap, int dim, int64_t j0, int64_t n, double *inorm) {
     for (int64_t j = j0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < j0 + n; j += (int64_t)gridDim.x * blockDim.x) {
         double s = 0;
         for (int k = 0; k < dim; ++k) {
             const double x = vec[(int64_t)k * cap + j];
             s = fma(x, x, s);
         }
-        norm[j] = sqrt(s);
+        inorm[j] = 1.0 / sqrt(s);
     }
 }
 
 // queries arrive as the columns of a dim x nq row-major matrix; they are repacked into chunks of QB queries,
 // qpack[(chunk*dim + k)*QB + qi] (zero padded), so that a chunk's [dim][QB] block is one contiguous shared-memory
-// image; qnorm[q] = Euclidean norm of query q
-__global__ void index_pack_queries_kernel(const double *q, int64_t ldq, int dim, int nq, int QB, double *qpack, double *qnorm) {
+// image; qinorm[q] = 1 / Euclidean norm of query q
+__global__ void index_pack_queries_kernel(const double *q, int64_t ldq, int dim, int nq, int QB, double *qpack, double *qinorm) {
     const int nchunks = (nq + QB - 1) / QB;
     const int64_t total = (int64_t)nchunks * dim * QB;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -81,15 +82,15 @@ __global__ void index_pack_queries_kernel(const double *q, int64_t ldq, int dim,
             const double x = q[(int64_t)k * ldq + qq];
             s = fma(x, x, s);
         }
-        qnorm[qq] = sqrt(s);
+        qinorm[qq] = 1.0 / sqrt(s);
     }
 }
 
 struct ScanArgs {
     const double *vec;
-    const double *norm;
+    const double *inorm;   // 1 / norm of the indexed vectors
     const double *qpack;
-    const double *qnorm;
+    const double *qinorm;  // 1 / norm of the queries
     uint64_t *keys;  // [nq][n]
     int64_t cap, n;
     int dim, nq, comparer;
@@ -107,16 +108,15 @@ __device__ __forceinline__ double acc_step(double acc, double x, double q) {
     return acc + (q != x ? 1.0 : 0.0);
 }
 
-__device__ __forceinline__ double finish_distance(int comparer, double acc, double nq_, double nx, int dim) {
+// comparer value from the accumulated sum.  The cosine family divides by the norms through their stored reciprocals
+// (comparisons.go:28 computes dot / (norma * normb); the product of reciprocals differs by rounding only) and a zero
+// norm yields NaN as in comparisons.go:24-26.  The cheap finishes are inlined -- a thread finishes up to 64 values per
+// vector tile -- the rest share one out-of-line copy.
+__device__ __noinline__ double finish_slow(int comparer, double acc, double iq, double ix, int dim) {
     switch (comparer) {
-        case COSINE_SIMILARITY:
-            return (nq_ == 0 || nx == 0) ? nan("") : acc / (nq_ * nx);
-        case COSINE_DISTANCE:
-            return (nq_ == 0 || nx == 0) ? nan("") : 1.0 - acc / (nq_ * nx);
         case ANGULAR_DISTANCE:
         case ANGULAR_SIMILARITY: {
-            if (nq_ == 0 || nx == 0) return nan("");
-            double c = acc / (nq_ * nx);
+            double c = acc * iq * ix;  // NaN for a zero vector
             if (c > 1) c = 1.0;
             const double a = acos(c) / 3.14159265358979323846;
             return comparer == ANGULAR_DISTANCE ? a : 1.0 - a;
@@ -125,13 +125,16 @@ __device__ __forceinline__ double finish_distance(int comparer, double acc, doub
             return acc / (double)dim;
         case HAMMING_SIMILARITY:
             return 1.0 - acc / (double)dim;
-        case EUCLIDEAN_DISTANCE:
-            return sqrt(acc);
-        case MANHATTEN_DISTANCE:
-            return acc;
         default:  // VECTOR_LEN_SIMILARITY
             return acc == 0 ? nan("") : sqrt(acc);
     }
+}
+__device__ __forceinline__ double finish_distance(int comparer, double acc, double iq, double ix, int dim) {
+    if (comparer == COSINE_DISTANCE) return 1.0 - acc * iq * ix;
+    if (comparer == COSINE_SIMILARITY) return acc * iq * ix;
+    if (comparer == EUCLIDEAN_DISTANCE) return sqrt(acc);
+    if (comparer == MANHATTEN_DISTANCE) return acc;
+    return finish_slow(comparer, acc, iq, ix, dim);
 }
 
 // distance(query, vector) for QB queries x all vectors: grid.y = query chunk, a thread owns a vector.  The chunk's
@@ -193,13 +196,159 @@ __global__ void __launch_bounds__(256) index_scan_kernel(const ScanArgs a) {
             }
         }
         if (live) {
-            const double nx = a.norm[j];
+            const double nx = a.inorm[j];
 #pragma unroll
             for (int qi = 0; qi < QB; ++qi) {
                 const int qq = chunk * QB + qi;
-                if (qq < a.nq) a.keys[(int64_t)qq * a.n + j] = dist_to_key(finish_distance(a.comparer, acc[qi], a.qnorm[qq], nx, a.dim));
+                if (qq < a.nq) a.keys[(int64_t)qq * a.n + j] = dist_to_key(finish_distance(a.comparer, acc[qi], a.qinorm[qq], nx, a.dim));
             }
         }
+    }
+}
+
+// ---- the batched scan for the dot-product comparers: FP64 tensor cores fed by TMA bulk copies -----------------------
+// Many queries against all vectors IS a dense contraction, keys = f(Q^T [nq x dim] . X [dim x n]), and the kernel above
+// shows what happens without tensor cores: at 16 queries per pass it is bound by the FP64 pipe (measured 5.5e12
+// multiply-adds/s whatever the blocking -- 1, 2 or 4 vectors per thread, vectors staged through shared memory or not),
+// 0.43 of the HBM roofline.  tcgen05 has no FP64 kind, so the contraction uses mma.sync.m8n8k4.f64 (DMMA):
+//   A = 8 queries x 4 dims (row major, from the query block in shared memory)
+//   B = 4 dims x 8 vectors (column major == the [dim][n] layout of the index, from the staged tile)
+//   D = 8 x 8 comparer numerators, two per thread, accumulated over dim in registers.
+// A warp owns 32 vectors x all QB = 8*MT queries of the pass; a persistent CTA of 8 warps per SM walks the
+// (vector tile, row tile) pairs in order while one elected thread keeps a STAGES-deep ring of [KT rows][256 vectors]
+// tiles in flight with cp.async.bulk (one 2 KB copy per row, completion on an mbarrier per stage).  Row pitches are
+// padded by 4 doubles so that both fragment reads touch all 32 banks exactly once per half-warp.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, unsigned bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+constexpr int MMA_TV = 256;            // vectors per CTA tile (8 warps x 32); the index capacity is a multiple of it
+constexpr int MMA_KT = 12;             // rows per stage (a multiple of 4)
+constexpr int MMA_STAGES = 3;
+constexpr int MMA_PITCH = MMA_TV + 4;  // doubles
+__host__ __device__ constexpr int mma_q_pitch(int dim) { return (dim + 15) / 16 * 16 + 4; }
+__host__ __device__ constexpr size_t scan_mma_smem_bytes(int dim, int QB) {
+    return (size_t)MMA_STAGES * MMA_KT * MMA_PITCH * 8 + (size_t)QB * mma_q_pitch(dim) * 8 + MMA_STAGES * 8;
+}
+
+template <int MT>  // QB = 8*MT queries per pass; dot-product comparers only; dim % 4 == 0
+__global__ void __launch_bounds__(256, 1) index_scan_mma_kernel(const ScanArgs a) {
+    constexpr int QB = 8 * MT;
+    extern __shared__ __align__(128) unsigned char scan_smem[];
+    double *xs = reinterpret_cast<double *>(scan_smem);                    // [STAGES][KT][PITCH]
+    double *qs = xs + MMA_STAGES * MMA_KT * MMA_PITCH;                     // [QB][PQ]
+    const int PQ = mma_q_pitch(a.dim);
+    uint64_t *full = reinterpret_cast<uint64_t *>(qs + (size_t)QB * PQ);   // [STAGES]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int chunk = blockIdx.y;
+    const int64_t nvt = (a.n + MMA_TV - 1) / MMA_TV;
+    const int nkt = (a.dim + MMA_KT - 1) / MMA_KT;
+    const int64_t my_tiles = (int64_t)blockIdx.x < nvt ? (nvt - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t total = my_tiles * nkt;  // pipeline steps of this CTA: (vector tile, row tile) pairs in order
+
+    if (tid == 0) {
+        for (int s = 0; s < MMA_STAGES; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    const double *qsrc = a.qpack + (int64_t)chunk * a.dim * QB;  // [dim][QB]
+    for (int i = tid; i < a.dim * QB; i += 256) qs[(i % QB) * PQ + i / QB] = qsrc[i];
+    __syncthreads();
+
+    // warp 0 issues a stage: lane r copies row r, lane 0 arms the barrier with the byte count of the whole stage
+    auto issue = [&](int64_t s) {
+        const int64_t vt = blockIdx.x + (s / nkt) * gridDim.x;
+        const int k0 = (int)(s % nkt) * MMA_KT;
+        const int rows = min(MMA_KT, a.dim - k0);
+        const int stage = (int)(s % MMA_STAGES);
+        if (lane == 0) mbar_expect_tx(&full[stage], (unsigned)rows * MMA_TV * 8u);
+        __syncwarp();
+        const double *src = a.vec + (int64_t)k0 * a.cap + vt * MMA_TV;
+        double *dst = xs + (size_t)stage * MMA_KT * MMA_PITCH;
+        if (lane < rows) bulk_g2s(dst + lane * MMA_PITCH, src + (int64_t)lane * a.cap, MMA_TV * 8u, &full[stage]);
+    };
+    if (warp == 0)
+        for (int64_t s = 0; s < MMA_STAGES && s < total; ++s) issue(s);
+
+    double acc[MT][4][2];
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+    const double *qfrag = qs + (size_t)g * PQ + t;             // + mt*8*PQ + k
+    for (int64_t s = 0; s < total; ++s) {
+        const int stage = (int)(s % MMA_STAGES);
+        const unsigned parity = (unsigned)((s / MMA_STAGES) & 1);
+        while (!mbar_try_wait(&full[stage], parity)) {
+        }
+        const int kt = (int)(s % nkt);
+        const int k0 = kt * MMA_KT;
+        const int rows = min(MMA_KT, a.dim - k0);
+        const double *xfrag = xs + (size_t)stage * MMA_KT * MMA_PITCH + t * MMA_PITCH + warp * 32 + g;  // + kk*PITCH + nt*8
+#pragma unroll
+        for (int kk = 0; kk < MMA_KT; kk += 4) {
+            if (kk < rows) {
+                double bf[4], af[MT];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) bf[nt] = xfrag[kk * MMA_PITCH + nt * 8];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) af[mt] = qfrag[(size_t)mt * 8 * PQ + k0 + kk];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(acc[mt][nt][0], acc[mt][nt][1], af[mt], bf[nt]);
+            }
+        }
+        if (kt == nkt - 1) {  // this vector tile is complete
+            const int64_t jw = (blockIdx.x + (s / nkt) * gridDim.x) * MMA_TV + warp * 32 + 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int64_t j = jw + nt * 8 + i;
+                    if (j < a.n) {
+                        const double nx = a.inorm[j];
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const int qq = chunk * QB + mt * 8 + g;
+                            if (qq < a.nq)
+                                a.keys[(int64_t)qq * a.n + j] = dist_to_key(finish_distance(a.comparer, acc[mt][nt][i], a.qinorm[qq], nx, a.dim));
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = 0.0;
+        }
+        __syncthreads();  // every warp has read this stage: it may be refilled
+        if (warp == 0 && s + MMA_STAGES < total) issue(s + MMA_STAGES);
     }
 }
 

@@ -131,10 +131,11 @@ class LinearScanIndex:
         return ids, dist, found
 
     def LastSearchTime(self):
-        """(scan ms, select ms, kernel launches) of the last search, CUDA events on the index's stream"""
-        a, b, n = C.c_float(0), C.c_float(0), C.c_int32(0)
-        _lib.lib().lda_b200_index_last_search_time(self._h, C.byref(a), C.byref(b), C.byref(n))
-        return a.value, b.value, n.value
+        """(scan ms, select ms, kernel launches, passes over the index) of the last search, CUDA events on the index's
+        stream"""
+        a, b, n, p = C.c_float(0), C.c_float(0), C.c_int32(0), C.c_int32(0)
+        _lib.lib().lda_b200_index_last_search_time(self._h, C.byref(a), C.byref(b), C.byref(n), C.byref(p))
+        return a.value, b.value, n.value, p.value
 
 
 def NewLinearScanIndex(compareFN, device=0):

@@ -95,15 +95,17 @@ def _check_against_oracle(comparer, m, queries, k, ids=None):
     return got_all
 
 
+@pytest.mark.parametrize("dim", [37, 64])   # 64: the dot-product comparers take the FP64 tensor-core kernel (dim % 4 == 0)
 @pytest.mark.parametrize("comparer", pairwise.ALL, ids=lambda c: c.name)
-def test_every_comparer_matches_the_oracle(comparer):
+def test_every_comparer_matches_the_oracle(comparer, dim):
     rng = np.random.default_rng(5)
-    m = rng.random((37, 300))
+    m = rng.random((dim, 300))
     if comparer.name.startswith("Hamming"):
-        m = rng.integers(0, 3, (37, 300)).astype(float)
-    q = m[:, rng.integers(0, 300, 9)] if comparer.name.startswith("Hamming") else rng.random((37, 9))
+        m = rng.integers(0, 3, (dim, 300)).astype(float)
+    q = m[:, rng.integers(0, 300, 9)] if comparer.name.startswith("Hamming") else rng.random((dim, 9))
     q[:, 0] = m[:, 17]
     _check_against_oracle(comparer, m, q, 11)
+    _check_against_oracle(comparer, m, q[:, :3], 4)     # few queries: the plain kernel
 
 
 @pytest.mark.parametrize("dim,n,nq,k", [(1, 50, 3, 5), (3, 5000, 1, 1), (256, 3000, 16, 10), (256, 3000, 17, 64),
