@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -54,6 +55,14 @@ struct Corpus {
     std::vector<cudaEvent_t> range_ev;
     bool ind_deferred = false;
     double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
+    // where the entries come from (the caller's arrays, valid for the duration of the call) and the local indptr: data
+    // movement can be issued per range of local documents (upload_part)
+    std::vector<int64_t> lp;
+    const int64_t *src_indptr = nullptr, *src_ind = nullptr;
+    const double *src_data = nullptr;
+    bool src_device = false;
+    int64_t W = 0;
+    int64_t range_docs = 0;  // > 0: Transform streams the corpus in ranges of this many local documents
 };
 
 // a term x document matrix converted to CSC on the device (from CSR or dense input); word ids ascending inside a document
@@ -113,6 +122,7 @@ struct lda_b200_handle {
 
     // streaming of the result during the last iteration of lda_b200_fit (second stream)
     cudaStream_t copy_stream = nullptr;
+    cudaStream_t down_stream = nullptr;  // device -> host leg of the Transform pipeline
     cudaEvent_t copy_ev = nullptr;
     double *pending_theta_out = nullptr;  // caller's K x D buffer, set by lda_b200_fit for the duration of the call
     double *dout = nullptr;               // K x Dl normalised, transposed result on the device
@@ -257,7 +267,8 @@ int validate_config(lda_b200_handle *h, const lda_b200_config *c) {
 
 // ---- kernel dispatch on the topic width ------------------------------------------------------------
 template <bool FIT>
-int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order) {
+int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     const int vecs = a.Kp / 4;
     const int n_docs = a.doc_end - a.doc_begin;
     if (n_docs <= 0) return 0;
@@ -273,7 +284,7 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order) {
     auto narrow = [&](auto kern, int lanes) -> int {
         int grid;
         TRY(grid_of(kern, 32 / lanes, &grid));
-        kern<<<grid, 256, 0, h->stream>>>(a);
+        kern<<<grid, 256, 0, st>>>(a);
         KCHECK();
         return 0;
     };
@@ -285,7 +296,7 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order) {
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
         if (occ < 1) occ = 1;
         const int grid = (int)std::min<int64_t>(((int64_t)n_docs + 7) / 8, (int64_t)h->sms * occ);
-        kern<<<grid, 256, smem, h->stream>>>(a, order);
+        kern<<<grid, 256, smem, st>>>(a, order);
         KCHECK();
         return 0;
     };
@@ -658,19 +669,21 @@ int h2d(lda_b200_handle *h, void *dst, const void *src, size_t bytes, cudaStream
 
 // device -> host of `rows` rows of `width` bytes (source pitch spitch, destination pitch dpitch); returns after the data
 // is in the caller's memory
-int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows) {
+int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows,
+           cudaStream_t st = nullptr) {
+    if (!st) st = h->stream;
     if (width == 0 || rows == 0) return 0;
     if (!is_pageable(dst)) {
-        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         return 0;
     }
     TRY(ensure_pin_ring(h));
     const size_t sb = lda_b200_handle::kStageSlotBytes;
     const size_t rows_per = std::max<size_t>(1, sb / width);
     if (width > sb) {  // very wide rows: let the driver stage them
-        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
         return 0;
     }
     struct Pending {
@@ -685,8 +698,18 @@ int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t
         if (dpitch == width) {
             threaded_memcpy((char *)dst + p.r0 * dpitch, h->pin_slot[p.slot], p.n * width, h->host_threads);
         } else {
-            for (size_t r = 0; r < p.n; ++r)
-                memcpy((char *)dst + (p.r0 + r) * dpitch, (const char *)h->pin_slot[p.slot] + r * width, width);
+            // strided destination (a column range of the caller's K x D matrix): rows split over the host threads -- a
+            // freshly allocated result is faulted in by these writes, and the faults dominate when one thread takes them
+            char *d0 = (char *)dst + p.r0 * dpitch;
+            const char *s0 = (const char *)h->pin_slot[p.slot];
+            const int nt = (int)std::min<size_t>((size_t)std::max(1, h->host_threads), p.n);
+            auto rows_of = [=](int t) {
+                for (size_t r = (size_t)t; r < p.n; r += (size_t)nt) memcpy(d0 + r * dpitch, s0 + r * width, width);
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nt; ++t) pool.emplace_back(rows_of, t);
+            rows_of(0);
+            for (std::thread &t : pool) t.join();
         }
         return 0;
     };
@@ -695,9 +718,9 @@ int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t
         const int slot = i % lda_b200_handle::kStageSlots;
         if ((int)inflight.size() == lda_b200_handle::kStageSlots) TRY(drain_one());
         const size_t n = std::min(rows_per, rows - r0);
-        CU(cudaMemcpy2DAsync(h->pin_slot[slot], width, (const char *)src + r0 * spitch, spitch, width, n, cudaMemcpyDeviceToHost,
-                             h->stream));
-        CU(cudaEventRecord(h->pin_done[slot], h->stream));
+        CU(cudaEventSynchronize(h->pin_done[slot]));  // an upload on another stream may still be reading the slot
+        CU(cudaMemcpy2DAsync(h->pin_slot[slot], width, (const char *)src + r0 * spitch, spitch, width, n, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(h->pin_done[slot], st));
         inflight.push_back({slot, r0, n});
     }
     while (!inflight.empty()) TRY(drain_one());
@@ -719,18 +742,57 @@ int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const doub
     return 0;
 }
 
+// Entries of the local documents [la, lb) -> c.val / c.ind on stream st: the caller's slices of the owning segments go
+// through the stage buffer (host sources) or are read in place (device sources); values float64 -> fp32, word ids
+// int64 -> int32 with the range check of narrow_ind_kernel.
+int upload_part(lda_b200_handle *h, Corpus &c, int64_t la, int64_t lb, cudaStream_t st, bool values, bool ids) {
+    const int64_t chunk = c.src_device ? ((int64_t)1 << 40) : (int64_t)(h->stage_bytes / 8);
+    for (const Segment &s : c.segs) {
+        const int64_t a = std::max(la, s.l0), b = std::min(lb, s.l0 + (s.g1 - s.g0));
+        if (a >= b) continue;
+        const int64_t p0 = c.src_indptr[s.g0 + (a - s.l0)], p1 = c.src_indptr[s.g0 + (b - s.l0)];
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 0 ? !values : !ids) continue;
+            const char *src = pass == 0 ? (const char *)c.src_data : (const char *)c.src_ind;
+            for (int64_t p = p0; p < p1; p += chunk) {
+                const int64_t n = std::min(chunk, p1 - p);
+                const void *dsrc = src + p * 8;  // 8-byte source elements where a kernel can read them
+                if (!c.src_device) {
+                    TRY(h2d(h, h->stage, src + p * 8, (size_t)n * 8, st));
+                    dsrc = h->stage;
+                }
+                const int64_t off = c.lp[(size_t)a] + (p - p0);
+                if (pass == 0)
+                    narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const double *)dsrc, c.val + off, n);
+                else
+                    narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const int64_t *)dsrc, c.ind + off, n, c.W, h->err_flag);
+                KCHECK();
+            }
+        }
+    }
+    return 0;
+}
+
 // Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
 // src_device: ind / data are device arrays (a matrix converted on the device, see DeviceCSC); indptr is always on the host.
+// range_docs > 0 (Transform / Perplexity): only the plan is made here -- local indptr, launch order per range of
+// range_docs documents -- and the entries follow range by range (upload_part) while earlier ranges compute.
 int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                   const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order,
-                  bool defer_ind = false, bool src_device = false) {
+                  bool defer_ind = false, bool src_device = false, int64_t range_docs = 0) {
     if (src_device) defer_ind = false;  // nothing crosses PCIe: no transfer to hide behind the first launches
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
     PhaseTimer pt(h->stream);
     free_corpus(h, c);
     c.D = D;
+    c.W = W;
     c.b = h->cfg.batch_size;
+    c.src_indptr = indptr;
+    c.src_ind = ind;
+    c.src_data = data;
+    c.src_device = src_device;
+    c.range_docs = range_docs;
     // the reference runs `Processes` minibatches concurrently (lda.go:487-528); here R GPUs x conc per GPU
     c.conc = per_minibatch_order ? std::min(MAX_CONCURRENT_MB, std::max(1, h->cfg.processes / h->nranks)) : 1;
     c.segs = make_segments(D, c.b, h->rank, h->nranks);
@@ -739,8 +801,8 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     c.Dl = Dl;
     if (Dl > 0x7fffffffLL) return fail(h, LDA_B200_EUNSUPPORTED, "more than 2^31 documents per GPU");
 
-    std::vector<int64_t> lp((size_t)Dl + 1);
-    lp[0] = 0;
+    std::vector<int64_t> &lp = c.lp;
+    lp.assign((size_t)Dl + 1, 0);
     for (const Segment &s : c.segs) {
         for (int64_t g = s.g0; g < s.g1; ++g) {
             const int64_t n = indptr[g + 1] - indptr[g];
@@ -759,55 +821,18 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     TRY(dalloc(h, &c.wc, (size_t)Dl));
     CU(cudaMemcpyAsync(c.doc_ptr, lp.data(), ((size_t)Dl + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemsetAsync(h->err_flag, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(h->dacc + 1, 0, sizeof(double), h->stream));
     pt.lap("ingest: cudaMalloc corpus");
 
-    const int64_t chunk = src_device ? ((int64_t)1 << 40) : (int64_t)(h->stage_bytes / 8);
-    // 8-byte source elements [p, p+n) where a kernel can read them: in place for device sources, else through the stage
-    auto staged = [&](const void *src, int64_t p, int64_t n, cudaStream_t st, const void **dev) -> int {
-        if (src_device) {
-            *dev = (const char *)src + p * 8;
-            return 0;
-        }
-        TRY(h2d(h, h->stage, (const char *)src + p * 8, (size_t)n * 8, st));
-        *dev = h->stage;
-        return 0;
-    };
+    const bool streamed = range_docs > 0;
     // values first: wc and wordsInCorpus (needed by the first M-step) depend only on them
-    for (const Segment &s : c.segs) {
-        const int64_t p0 = indptr[s.g0], p1 = indptr[s.g1];
-        const int64_t l0 = lp[s.l0];
-        for (int64_t p = p0; p < p1; p += chunk) {
-            const int64_t n = std::min(chunk, p1 - p);
-            const void *dsrc;
-            TRY(staged(data, p, n, h->stream, &dsrc));
-            narrow_val_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>((const double *)dsrc, c.val + l0 + (p - p0), n);
-            KCHECK();
-        }
-    }
-    // word ids of the local documents [la, lb): host slices of the owning segments -> c.ind, on stream st
-    auto upload_ind = [&](int64_t la, int64_t lb, cudaStream_t st) -> int {
-        for (const Segment &s : c.segs) {
-            const int64_t a = std::max(la, s.l0), b = std::min(lb, s.l0 + (s.g1 - s.g0));
-            if (a >= b) continue;
-            const int64_t p0 = indptr[s.g0 + (a - s.l0)], p1 = indptr[s.g0 + (b - s.l0)];
-            for (int64_t p = p0; p < p1; p += chunk) {
-                const int64_t n = std::min(chunk, p1 - p);
-                const void *dsrc;
-                TRY(staged(ind, p, n, st, &dsrc));
-                narrow_ind_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, st>>>((const int64_t *)dsrc, c.ind + lp[a] + (p - p0), n, W,
-                                                                               h->err_flag);
-                KCHECK();
-            }
-        }
-        return 0;
-    };
-    if (!defer_ind) TRY(upload_ind(0, Dl, h->stream));
-    {   // Longest-first processing order inside every launch range (`conc` minibatches for Fit, everything for
-        // Transform), by a stable counting sort on the document length; runs on the host while the copies above are
-        // in flight.
+    if (!streamed) TRY(upload_part(h, c, 0, Dl, h->stream, true, !defer_ind));
+    {   // Longest-first processing order inside every launch range (`conc` minibatches for Fit, range_docs documents
+        // or everything for Transform), by a stable counting sort on the document length; runs on the host while the
+        // copies above are in flight.
         std::vector<int> ord((size_t)Dl);
         std::vector<int> cnt;
-        const int64_t blk = per_minibatch_order ? c.b * c.conc : std::max<int64_t>(Dl, 1);
+        const int64_t blk = per_minibatch_order ? c.b * c.conc : streamed ? range_docs : std::max<int64_t>(Dl, 1);
         for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
             const int64_t l1 = std::min(Dl, l0 + blk);
             int64_t maxlen = 0;
@@ -819,10 +844,10 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         }
         TRY(dalloc(h, &c.order, (size_t)Dl));
         CU(cudaMemcpyAsync(c.order, ord.data(), (size_t)Dl * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaStreamSynchronize(h->stream));  // ord / lp are host temporaries
+        CU(cudaStreamSynchronize(h->stream));  // ord is a host temporary
     }
     pt.lap("ingest: H2D + narrow + length sort");
-    CU(cudaMemsetAsync(h->dacc + 1, 0, sizeof(double), h->stream));
+    if (streamed) return 0;
     if (Dl > 0) {
         doc_wc_kernel<<<grid_for(Dl * 32, 256, h->sms * 8), 256, 0, h->stream>>>(c.doc_ptr, c.val, (int)Dl, c.wc, wc64_out, h->dacc + 1);
         KCHECK();
@@ -843,7 +868,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         CU(cudaEventRecord(h->copy_ev, h->stream));
         CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
         for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
-            TRY(upload_ind(l0, std::min(Dl, l0 + blk), h->copy_stream));
+            TRY(upload_part(h, c, l0, std::min(Dl, l0 + blk), h->copy_stream, false, true));
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c.range_ev.push_back(e);
@@ -979,28 +1004,187 @@ DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
 
 inline double rho_calc(const lda_b200_schedule &s, double t) { return s.S / pow(s.Tau + t, s.Kappa); }  // lda.go:30-32
 
-// unNormalisedTransform (lda.go:420-437) on an uploaded corpus
-int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, int32_t *passes_out_host) {
+// unNormalisedTransform (lda.go:420-437) and, when theta_out is given, normaliseTheta + the transposed float64 copy of
+// lda.go:452, over a corpus whose plan is in place (upload_corpus).  A corpus planned with range_docs > 0 flows through
+// three streams range by range -- raw entries in (copy stream: copy engine only), narrowing + wc + burnInDoc kernel +
+// normalise/transpose (main stream), result out (down stream) -- so the host<->device transfers
+// of neighbouring ranges hide behind the kernel of the current one; otherwise it is one launch over all documents.  Documents are independent (lda.go:429-435), so the split changes
+// nothing but the longest-first order inside a launch.
+int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *theta_out, int32_t *passes_out_host) {
     const int T = h->cfg.transformation_passes;
     TRY(fill_rho_table(h, rho_theta_t, T + 1));
+    const bool streamed = c.range_docs > 0;
+    const int64_t Dl = c.Dl, blk = streamed ? c.range_docs : std::max<int64_t>(Dl, 1);
     int32_t *dpass = nullptr;
-    if (passes_out_host) TRY(dalloc(h, &dpass, (size_t)c.Dl));
-    CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
-    DocsArgs a = docs_args(h, c, T);
-    a.passes_out = dpass;
-    int rc = launch_docs<false>(h, a, c.order);
-    if (!rc && passes_out_host) {
-        std::vector<int32_t> tmp((size_t)c.Dl);
-        cudaError_t e = cudaMemcpyAsync(tmp.data(), dpass, (size_t)c.Dl * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "passes read-back failed: %s", cudaGetErrorString(e));
-        for (const Segment &s : c.segs)
-            for (int64_t g = s.g0; g < s.g1 && !rc; ++g) passes_out_host[g] = tmp[(size_t)(s.l0 + g - s.g0)];
+    double *dout = nullptr;
+    int64_t *raw[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev;  // per range: entries uploaded, narrowed, result ready
+    auto new_event = [&](cudaEvent_t *e) -> int {
+        CU(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        ev.push_back(*e);
+        return 0;
+    };
+    struct Range {
+        int64_t la, lb;
+        cudaEvent_t done;
+    };
+    auto download = [&](const Range &r) -> int {  // columns of the documents [la, lb) of the K x D result
+        CU(cudaStreamWaitEvent(h->down_stream, r.done, 0));
+        if (getenv("LDA_B200_TIMING")) {
+            const double t0 = PhaseTimer::now();
+            cudaEventSynchronize(r.done);
+            fprintf(stderr, "[lda_b200] transform download waited %8.2f ms for the range's kernels\n", 1e3 * (PhaseTimer::now() - t0));
+        }
+        for (const Segment &s : c.segs) {
+            const int64_t a = std::max(r.la, s.l0), b = std::min(r.lb, s.l0 + (s.g1 - s.g0));
+            if (a >= b) continue;
+            TRY(d2h_2d(h, theta_out + s.g0 + (a - s.l0), (size_t)c.D * sizeof(double), dout + a, (size_t)Dl * sizeof(double),
+                       (size_t)(b - a) * sizeof(double), (size_t)h->K, h->down_stream));
+        }
+        return 0;
+    };
+    auto run = [&]() -> int {
+        if (passes_out_host) TRY(dalloc(h, &dpass, (size_t)Dl));
+        if (theta_out && Dl > 0) TRY(dalloc(h, &dout, (size_t)h->K * Dl));
+        if (streamed) {  // the copy stream starts once everything queued so far has run
+            CU(cudaEventRecord(h->copy_ev, h->stream));
+            CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
+        }
+        DocsArgs a = docs_args(h, c, T);
+        a.passes_out = dpass;
+        Range prev{0, 0, nullptr};
+        bool have_prev = false;
+        // Host sources: the copy engine alone brings a range's raw entries (int64 ids, float64 values) into one of two
+        // staging buffers; the narrowing and wc kernels run on the main stream in front of the range's launch.  (Run
+        // on the copy stream they would wait for SM resources until the previous range's persistent kernel drains,
+        // and the transfer they gate would not overlap anything.)
+        const bool raw_staging = streamed && !c.src_device;
+        int64_t max_nnz = 0;
+        for (int64_t la = 0; la < Dl; la += blk) max_nnz = std::max(max_nnz, c.lp[(size_t)std::min(Dl, la + blk)] - c.lp[(size_t)la]);
+        if (raw_staging)
+            for (int i = 0; i < 2; ++i) TRY(dalloc(h, &raw[i], (size_t)2 * std::max<int64_t>(max_nnz, 1)));
+        std::vector<cudaEvent_t> narrowed;  // per range: its staging buffer may be overwritten
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ktime;
+        const bool trace = getenv("LDA_B200_TIMING") != nullptr;
+        const double t_start = PhaseTimer::now();
+        auto stamp = [&](const char *what, int64_t range) {
+            if (trace) fprintf(stderr, "[lda_b200] transform range %2lld %-22s at %8.2f ms\n", (long long)range, what, 1e3 * (PhaseTimer::now() - t_start));
+        };
+        int64_t r = 0;
+        for (int64_t la = 0; la < Dl; la += blk, ++r) {
+            const int64_t lb = std::min(Dl, la + blk);
+            const int64_t n_r = c.lp[(size_t)lb] - c.lp[(size_t)la];
+            cudaStream_t cs = h->stream;
+            if (raw_staging) {
+                int64_t *ids_raw = raw[r & 1];
+                double *val_raw = reinterpret_cast<double *>(raw[r & 1] + max_nnz);
+                if (r >= 2) CU(cudaStreamWaitEvent(h->copy_stream, narrowed[(size_t)(r - 2)], 0));
+                for (const Segment &sg : c.segs) {  // the caller's slices of the owning segments, back to back
+                    const int64_t sa = std::max(la, sg.l0), sb = std::min(lb, sg.l0 + (sg.g1 - sg.g0));
+                    if (sa >= sb) continue;
+                    const int64_t p0 = c.src_indptr[sg.g0 + (sa - sg.l0)], p1 = c.src_indptr[sg.g0 + (sb - sg.l0)];
+                    const int64_t off = c.lp[(size_t)sa] - c.lp[(size_t)la];
+                    TRY(h2d(h, ids_raw + off, c.src_ind + p0, (size_t)(p1 - p0) * 8, h->copy_stream));
+                    TRY(h2d(h, val_raw + off, c.src_data + p0, (size_t)(p1 - p0) * 8, h->copy_stream));
+                }
+                cudaEvent_t up;
+                TRY(new_event(&up));
+                CU(cudaEventRecord(up, h->copy_stream));
+                CU(cudaStreamWaitEvent(cs, up, 0));
+                stamp("upload issued", r);
+                if (n_r > 0) {
+                    narrow_val_kernel<<<grid_for(n_r, 256, h->sms * 8), 256, 0, cs>>>(val_raw, c.val + c.lp[(size_t)la], n_r);
+                    KCHECK();
+                    narrow_ind_kernel<<<grid_for(n_r, 256, h->sms * 8), 256, 0, cs>>>(ids_raw, c.ind + c.lp[(size_t)la], n_r, c.W, h->err_flag);
+                    KCHECK();
+                }
+                cudaEvent_t nd;
+                TRY(new_event(&nd));
+                CU(cudaEventRecord(nd, cs));
+                narrowed.push_back(nd);
+            } else if (streamed) {
+                TRY(upload_part(h, c, la, lb, cs, true, true));  // device source: read in place
+            }
+            if (streamed) {
+                doc_wc_kernel<<<grid_for((lb - la) * 32, 256, h->sms * 8), 256, 0, cs>>>(c.doc_ptr + la, c.val, (int)(lb - la), c.wc + la,
+                                                                                              nullptr, h->dacc + 1);
+                KCHECK();
+            }
+            CU(cudaMemsetAsync(a.doc_counter, 0, sizeof(int), cs));
+            a.doc_begin = (int)la;
+            a.doc_end = (int)lb;
+            cudaEvent_t k0 = nullptr, k1 = nullptr;
+            if (trace) {
+                CU(cudaEventCreate(&k0));
+                CU(cudaEventCreate(&k1));
+                CU(cudaEventRecord(k0, cs));
+            }
+            TRY(launch_docs<false>(h, a, c.order, cs));
+            if (trace) {
+                CU(cudaEventRecord(k1, cs));
+                ktime.push_back({k0, k1});
+            }
+            if (dout) {
+                transpose_out_kernel<true><<<(unsigned)((lb - la + 31) / 32), 256, 0, cs>>>(c.theta + la * h->Kp, lb - la, h->K, h->Kp,
+                                                                                                  nullptr, dout + la, Dl);
+                KCHECK();
+                Range cur{la, lb, nullptr};
+                TRY(new_event(&cur.done));
+                CU(cudaEventRecord(cur.done, cs));
+                stamp("kernels launched", r);
+                if (have_prev) TRY(download(prev));  // while this range computes
+                stamp("previous downloaded", r);
+                prev = cur;
+                have_prev = true;
+            }
+        }
+        if (have_prev) TRY(download(prev));
+        if (streamed) {  // wordCount of Perplexity (lda.go:372-385) and ids that were out of range
+            if (h->nranks > 1) NC(nccl().AllReduce(h->dacc + 1, h->dacc + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
+            CU(cudaMemcpyAsync(h->h_pinned, h->dacc + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaMemcpyAsync(h->h_pinned + 1, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        }
+        if (passes_out_host) {
+            std::vector<int32_t> tmp((size_t)Dl);
+            CU(cudaMemcpyAsync(tmp.data(), dpass, (size_t)Dl * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+            CU(cudaStreamSynchronize(h->stream));
+            for (const Segment &s : c.segs)
+                for (int64_t g = s.g0; g < s.g1; ++g) passes_out_host[g] = tmp[(size_t)(s.l0 + g - s.g0)];
+        }
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaStreamSynchronize(h->down_stream));
+        for (size_t i = 0; i < ktime.size(); ++i) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ktime[i].first, ktime[i].second);
+            fprintf(stderr, "[lda_b200] transform range %2zu kernel %8.2f ms\n", i, ms);
+            cudaEventDestroy(ktime[i].first);
+            cudaEventDestroy(ktime[i].second);
+        }
+        if (streamed) {
+            c.n_global = h->h_pinned[0];
+            int bad;
+            memcpy(&bad, h->h_pinned + 1, sizeof(int));
+            if (bad) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)c.W);
+        }
+        return 0;
+    };
+    const int rc = run();
+    if (rc) {  // leave no work behind that still refers to the caller's arrays or to buffers freed below
+        cudaStreamSynchronize(h->copy_stream);
+        cudaStreamSynchronize(h->stream);
+        cudaStreamSynchronize(h->down_stream);
     }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
     if (dpass) cudaFreeAsync(dpass, h->stream);
+    if (dout) cudaFreeAsync(dout, h->stream);
+    for (int i = 0; i < 2; ++i)
+        if (raw[i]) cudaFreeAsync(raw[i], h->stream);
     return rc;
 }
 
+// documents per range of the Transform pipeline: enough for ~14 documents per resident warp, small enough that the
+// first upload and the last download (the parts no kernel hides) stay short
+constexpr int64_t kTransformRangeDocs = 65536;
 
 // ---- CSR / dense -> CSC on the device (sparse.ToCSC() lda.go:464-466; dense scan utils.go:51-57) -------------------
 void free_device_csc(lda_b200_handle *h, DeviceCSC &m) {
@@ -1214,6 +1398,7 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         h->sms = prop.multiProcessorCount;
         CU(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->down_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->copy_ev, cudaEventDisableTiming));
         cudaMemPool_t pool;
         CU(cudaDeviceGetDefaultMemPool(&pool, device));
@@ -1245,6 +1430,7 @@ void lda_b200_destroy(lda_b200_handle *h) {
     peer_teardown(h);
     if (h->comm) nccl().CommDestroy(h->comm);
     if (h->copy_stream) cudaStreamSynchronize(h->copy_stream);
+    if (h->down_stream) cudaStreamSynchronize(h->down_stream);
     dfree(h, &h->dout);
     free_corpus(h, h->fitc);
     dfree(h, &h->nphi);
@@ -1272,6 +1458,7 @@ void lda_b200_destroy(lda_b200_handle *h) {
     }
     if (h->copy_ev) cudaEventDestroy(h->copy_ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    if (h->down_stream) cudaStreamDestroy(h->down_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1712,15 +1899,10 @@ static int transform_impl(lda_b200_handle *h, int64_t D, const int64_t *indptr, 
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device);
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device, kTransformRangeDocs);
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
-    if (!rc) rc = run_transform(h, c, rho_theta_t, passes_out);
-    if (!rc) rc = write_theta_out(h, c, theta_out);
-    if (!rc) {
-        cudaError_t e = cudaStreamSynchronize(h->stream);
-        if (e != cudaSuccess) rc = fail(h, LDA_B200_ECUDA, "transform failed: %s", cudaGetErrorString(e));
-    }
+    if (!rc) rc = run_transform(h, c, rho_theta_t, theta_out, passes_out);
     free_corpus(h, c);
     return rc;
 }
@@ -1732,10 +1914,10 @@ static int perplexity_impl(lda_b200_handle *h, int64_t D, const int64_t *indptr,
     if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
     CU(cudaSetDevice(h->device));
     Corpus c;
-    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device);  // wordCount = c.n_global, lda.go:372-385
+    int rc = upload_corpus(h, c, h->W, D, indptr, ind, data, nullptr, false, false, src_device, kTransformRangeDocs);
     if (!rc) rc = init_theta(h, c, theta0, rnd, 0);
     if (!rc && !theta0) advance(rnd, (uint64_t)D * (uint64_t)h->K);
-    if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr);
+    if (!rc) rc = run_transform(h, c, rho_theta_t, nullptr, nullptr);   // also yields wordCount = c.n_global, lda.go:372-385
     if (!rc) rc = eval_perplexity(h, c, c.n_global, out);
     free_corpus(h, c);
     return rc;

@@ -72,11 +72,14 @@ elif a.case == "c5":
     m = CSC(W, Dt, *held)
     lda.Transform(CSC(W, 8192, held[0][:8193], held[1][:held[0][8192]], held[2][:held[0][8192]]))  # warm-up
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    theta, passes = lda.Transform(m, return_passes=True)
-    dt = time.perf_counter() - t0
+    times = []
+    for _ in range(3):       # the first call also grows the device memory pool to this corpus' size
+        t0 = time.perf_counter()
+        theta, passes = lda.Transform(m, return_passes=True)
+        times.append(time.perf_counter() - t0)
+    dt = min(times)
     lens = np.diff(held[0])
     visits = int((lens * np.maximum(passes, 0)).sum())
-    print(json.dumps(dict(case="c5", K=K, docs=Dt, nnz=int(held[0][-1]), seconds_e2e=dt, mean_passes=float(passes.mean()),
+    print(json.dumps(dict(case="c5", K=K, docs=Dt, nnz=int(held[0][-1]), seconds_e2e=dt, seconds_each_call=times, mean_passes=float(passes.mean()),
                           visits=visits, updates_per_s_e2e=visits * K / dt, docs_per_s=Dt / dt,
                           ok=bool(np.abs(theta.sum(0) - 1).max() < 1e-8))))
