@@ -8,7 +8,8 @@ A *step* is one SCVB0 iteration of lda.go:501-528 over the whole synthetic corpu
 burn-in + sufficient-statistics kernel, the allreduce (N > 1) and the rho-blend M-step.  Default workload is
 BASELINE.json configs[2] -- the configuration the metric is quoted on -- K = 256 topics, 1M documents x 100k words,
 ~200M non-zeros, Zipfian, BatchSize 8192 documents per GPU-minibatch; with N GPUs the same corpus is sharded by
-minibatch (strong scaling), one process per GPU, nPhiHat all-reduced with NCCL every step.
+minibatch (strong scaling), one process per GPU, nPhiHat reduced across the GPUs every step (one reduce + M-step kernel
+over NVLink peer memory; ncclAllReduce as fallback).
 
 value   = non-zero visits x K / time of K timed steps, inputs already resident in HBM, CUDA events on the launching
           stream, max over ranks.   unit: token-topic updates/s
@@ -294,6 +295,8 @@ def ours(args):
     perplexity = lda.PerplexityTrace[-1] if lda.PerplexityTrace else None
     lda.FitEnd(want_theta=False)
 
+    exchange = ("nPhiHat reduced + M-step in one kernel over NVLink peer memory per step" if lda.CommInfo()[2] else
+                "ncclAllReduce of nPhiHat + M-step per step") if world > 1 else "no exchange"
     peak, peak_src = measured_peak()
     kbytes = alg_bytes(nnz_local, docs_local, K, B) * steps      # what this rank's minibatch kernels processed
     achieved = kbytes / (mb_ms.value * 1e-3) / 1e9 if mb_ms.value > 0 else None
@@ -378,8 +381,8 @@ def ours(args):
             "config": {"workload": "%s: LDA SCVB0 fit, K=%d, %d docs x %d vocab, %d nnz (Zipfian planted-LDA corpus, seed 12345)"
                        % (cfgname, K, D, W, nnz), "batch_size": b, "processes": world * args.processes_per_gpu,
                        "burn_in_passes": B,
-                       "parallelism": "dp%d (minibatch m -> GPU m %% %d, %d minibatches per GPU per step, NCCL allreduce of "
-                                      "nPhiHat per step)" % (world, world, args.processes_per_gpu),
+                       "parallelism": "dp%d (minibatch m -> GPU m %% %d, %d minibatches per GPU per step, %s)" % (
+                           world, world, args.processes_per_gpu, exchange),
                        "step": "one SCVB0 iteration over all %d minibatches (%d launches per GPU)" % (
                            (D + b - 1) // b, -(-((D + b - 1) // b) // (world * args.processes_per_gpu))),
                        "l2": "inputs larger than L2 (CSC + nTheta = %.1f GB per GPU per step)" % (

@@ -188,3 +188,22 @@ def test_errors():
     with pytest.raises(TypeError):
         nlp_b200.NewLinearScanIndex(lambda a, b: 0.0)
     assert index.Search([1.0, 2.0], 1)[0].ID == 0   # still usable
+
+
+def test_committed_golden_vectors():
+    """tests/golden/index_golden.json: fixed targets for the CUDA path (generated by tests/golden/make_index_golden.py)"""
+    import json
+    import os
+    from tests.golden.make_index_golden import inputs
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "index_golden.json")))
+    by_name = {c.name: c for c in pairwise.ALL}
+    for case in g["cases"]:
+        m, q = inputs(case["seed"], case["dim"], case["n"], case["nq"])
+        assert float(m.sum() + q.sum()) == case["checksum"]
+        index = nlp_b200.NewLinearScanIndex(by_name[case["comparer"]])
+        index.IndexColumns(m, [100 + j for j in range(case["n"])])
+        got = index.SearchColumns(q, case["k"])
+        for i, want in enumerate(case["results"]):
+            assert [x.ID for x in got[i]] == want["ids"], case["comparer"]
+            assert np.abs(np.array([x.Distance for x in got[i]]) - np.array(want["distances"])).max() <= DIST_ATOL
+        index.Close()

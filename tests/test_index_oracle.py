@@ -92,3 +92,22 @@ def test_comparers_closed_form():
     for name in ("CosineSimilarity", "CosineDistance", "AngularDistance", "VectorLenSimilarity"):
         assert math.isnan(I.compare(name, a, z))
     assert I.compare("AngularDistance", a, a) == pytest.approx(0.0, abs=2e-8)
+
+
+def test_committed_golden_vectors_reproduce():
+    # tests/golden/index_golden.json (tests/golden/make_index_golden.py): the oracle and the input generator are stable
+    import json
+    import os
+    from tests.golden.make_index_golden import inputs
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "index_golden.json")))
+    assert len(g["cases"]) >= 6
+    for case in g["cases"]:
+        m, q = inputs(case["seed"], case["dim"], case["n"], case["nq"])
+        assert float(m.sum() + q.sum()) == case["checksum"]
+        index = I.LinearScanIndex(case["comparer"])
+        for j in range(case["n"]):
+            index.Index(m[:, j], 100 + j)
+        for i, want in enumerate(case["results"]):
+            got = sorted(index.Search(q[:, i], case["k"]))
+            assert [x.ID for x in got] == want["ids"]
+            assert np.allclose([x.Distance for x in got], want["distances"], rtol=0, atol=1e-15)

@@ -564,6 +564,44 @@ def test_medium_parity():
     assert tr[-1] < tr[0]
 
 
+@pytest.mark.parametrize("k", [8, 128])
+def test_transform_pipeline_ranges(k):
+    """Transform streams the corpus through the device in ranges of 65,536 documents (run_transform): several ranges,
+    the last one short, give exactly what separate calls on the pieces give (documents are independent,
+    lda.go:429-435), Perplexity agrees, and a sample of documents matches the oracle."""
+    D, W = 140_000, 3000
+    fit = synth(400, W, 30)
+    held = synth(D, W, 8, block=8192, seed=4242)
+    lda = new_lda(k, Iterations=5, BatchSize=100)
+    lda.Fit(fit)
+    rng = np.random.default_rng(1)
+    theta0 = rng.random((D, k))
+    whole, passes = lda.Transform(held, theta0=theta0, return_passes=True)
+    assert whole.shape == (k, D) and np.abs(whole.sum(0) - 1).max() <= 1e-8
+    cuts = [0, 50_000, 65_536, 131_072, D]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        sub = CSC(W, b - a, held.indptr[a:b + 1] - held.indptr[a], held.ind[held.indptr[a]:held.indptr[b]],
+                  held.data[held.indptr[a]:held.indptr[b]])
+        part, pp = lda.Transform(sub, theta0=theta0[a:b], return_passes=True)
+        assert np.array_equal(part, whole[:, a:b]) and np.array_equal(pp, passes[a:b]), (a, b)
+    # the same through the oracle on a sample that spans the range boundaries
+    nphi, nz = lda.GetState()
+    o = new_oracle(k)
+    o.set_state(nphi, nz)
+    o.rhoThetaT = lda.rhoThetaT
+    pick = np.r_[0:40, 65_516:65_556, D - 40:D]
+    ip = np.concatenate(([0], np.cumsum(np.diff(held.indptr)[pick])))
+    idx = np.concatenate([np.arange(held.indptr[j], held.indptr[j + 1]) for j in pick])
+    sample = (W, len(pick), ip.astype(np.int64), held.ind[idx], held.data[idx])
+    want, wp = o.Transform(sample, theta0=theta0[pick], return_passes=True)
+    same = wp == passes[pick]
+    assert same.mean() >= 0.95
+    assert np.abs(whole[:, pick][:, same] - want[:, same]).max() <= THETA_ATOL
+    # Perplexity runs the same pipeline without reading theta back
+    p1 = lda.Perplexity(held, theta0=theta0)
+    assert np.isfinite(p1) and p1 > 1
+
+
 def _full_size_properties(name, batch, processes, iters):
     import torch
     D, W, K, md = corpus_synth.shape(name)
