@@ -1,5 +1,5 @@
-"""The C++ host mirror (include/nlp_lda.hpp) and the reference's tests restated in C++ (tests/cpp/lda_test.cpp):
-compiled against liblda_b200.so on CPU, executed on the B200 box."""
+"""The C++ host mirrors (include/nlp_lda.hpp, include/nlp_index.hpp) and the reference's tests restated in C++
+(tests/cpp/lda_test.cpp, tests/cpp/index_test.cpp): compiled against liblda_b200.so on CPU, executed on the B200 box."""
 import os
 import subprocess
 
@@ -9,17 +9,19 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "lda_test")
 
 
-def build():
-    src = os.path.join(ROOT, "tests", "cpp", "lda_test.cpp")
+def build(name="lda_test"):
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
+    exe = os.path.join(ROOT, "tests", "cpp", name)
     libdir = os.path.join(ROOT, "nlp_b200")
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
            "-L", libdir, "-llda_b200", "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
-    return EXE
+    return exe
 
 
 def test_cpp_host_mirror_compiles_and_links():
     assert os.path.exists(build())
+    assert os.path.exists(build("index_test"))
 
 
 def test_cpp_host_fails_loudly_without_gpu():
@@ -28,10 +30,19 @@ def test_cpp_host_fails_loudly_without_gpu():
         pytest.skip("a GPU is present")
     r = subprocess.run([build()], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+    r = subprocess.run([build("index_test")], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CPU fallback" in r.stderr
 
 
 @pytest.mark.gpu
 def test_reference_tests_in_cpp():
     r = subprocess.run([build()], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASS" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_index_tests_in_cpp():
+    r = subprocess.run([build("index_test")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASS" in r.stdout
