@@ -16,6 +16,8 @@
 #include <utility>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges show up in Nsight Systems / ncu --nvtx, cost nothing without a tool attached
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -197,6 +199,15 @@ int fail(lda_b200_handle *h, int code, const char *fmt, ...) {
         h->launches++;                \
         CU(cudaPeekAtLastError());    \
     } while (0)
+
+// NVTX range for the lifetime of the object: the host-facing calls, each iteration, each step's launch and exchange /
+// M-step, each Transform range (the reference has no tracing hooks at all)
+struct Nvtx {
+    explicit Nvtx(const char *name) { nvtxRangePushA(name); }
+    ~Nvtx() { nvtxRangePop(); }
+    Nvtx(const Nvtx &) = delete;
+    Nvtx &operator=(const Nvtx &) = delete;
+};
 
 // LDA_B200_TIMING=1: wall-clock phases of the host-facing calls on stderr (diagnostic)
 struct PhaseTimer {
@@ -780,6 +791,7 @@ int upload_part(lda_b200_handle *h, Corpus &c, int64_t la, int64_t lb, cudaStrea
 int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int64_t *indptr, const int64_t *ind,
                   const double *data, double *wc64_out /*device, optional*/, bool per_minibatch_order,
                   bool defer_ind = false, bool src_device = false, int64_t range_docs = 0) {
+    Nvtx range("lda_b200: ingest corpus");
     if (src_device) defer_ind = false;  // nothing crosses PCIe: no transfer to hide behind the first launches
     if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
     if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
@@ -904,6 +916,7 @@ void advance(lda_b200_pcg *rnd, uint64_t draws) {
 
 // perplexity (lda.go:392-408) of the corpus under theta and the current nPhi, with denominator `sum`
 int eval_perplexity(lda_b200_handle *h, const Corpus &c, double sum, double *out) {
+    Nvtx range("lda_b200: perplexity");
     CU(cudaMemsetAsync(h->colsum, 0, (size_t)h->Kp * sizeof(double), h->stream));
     const int bs = blend_block(h->Kp);
     colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->colsum);
@@ -1074,6 +1087,7 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *the
         for (int64_t la = 0; la < Dl; la += blk, ++r) {
             const int64_t lb = std::min(Dl, la + blk);
             const int64_t n_r = c.lp[(size_t)lb] - c.lp[(size_t)la];
+            Nvtx t_range("lda_b200: transform range");
             cudaStream_t cs = h->stream;
             if (raw_staging) {
                 int64_t *ids_raw = raw[r & 1];
@@ -1653,6 +1667,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
     h->ev_used = 0;
 
     for (int it = 0; it < n_iterations && !h->stopped && h->it_done < cfg.iterations; ++it) {
+        Nvtx it_range("lda_b200: SCVB0 iteration");
         ctr->rho_theta_t += 1;  // lda.go:502
         TRY(fill_rho_table(h, ctr->rho_theta_t, B + 1));
         // last iteration of lda_b200_fit: stream the result out behind every launch
@@ -1683,6 +1698,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 a.hat_scale[l - l_first] = (float)(ctr->words_in_corpus / (double)b_actual * (n_s > 1 ? cg : 1.0));
             }
             if (l_first >= 0) {
+                Nvtx mb_range("lda_b200: minibatch launch (burn-in + sufficient statistics)");
                 a.doc_begin = (int)(l_first * b);
                 a.doc_end = (int)std::min<int64_t>(c.Dl, (l_last + 1) * b);
                 if (c.ind_deferred) CU(cudaStreamWaitEvent(h->stream, c.range_ev[(size_t)(l_first / c.conc)], 0));
@@ -1693,6 +1709,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 if (stream_out) TRY(stream_theta_range(h, c, a.doc_begin, a.doc_end));
             }
             const double Ad = A, Cd = (n_s > 1) ? 1.0 : c_single;
+            Nvtx m_range(h->peer_ok ? "lda_b200: exchange + M-step (peer memory)" : "lda_b200: exchange + M-step");
             if (h->peer_ok) {
                 // fused path: [barrier] -> reduce over peer memory + M-step on this rank's row slice -> [barrier + nZ]
                 BarrierArgs bar;
