@@ -516,6 +516,21 @@ def test_errors():
     with pytest.raises(_lib.LdaB200Error, match="BatchSize"):
         new_lda(3, BatchSize=0).Fit(FIXTURE_A)
     lda.Fit(FIXTURE_A)  # the handle is still usable after errors
+    # the same checks on the Transform / Perplexity pipeline and on the device-side CSR conversion
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.Transform(bad)
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.Perplexity(bad)
+    import scipy.sparse as sp
+    csr = sp.csr_matrix(FIXTURE_A)
+    bad_csr = CSR(9, 9, csr.indptr.astype(np.int64), csr.indices.astype(np.int64), csr.data.copy())
+    bad_csr.ind[2] = 9  # document id out of range
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.Transform(bad_csr)
+    with pytest.raises(_lib.LdaB200Error, match="non-decreasing"):
+        lda.Fit(as_csc(FIXTURE_A)._replace(indptr=np.array([0, 3, 2, 9, 12, 15, 18, 21, 24, 27], dtype=np.int64)))
+    t = lda.Transform(FIXTURE_A)
+    assert np.abs(t.sum(0) - 1).max() <= 1e-8  # still usable
 
 
 # ---- size-independent properties at a BASELINE-sized configuration -----------------------------------------------------
