@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # liblda_b200.so is a build artefact (git-ignored): a fresh checkout compiles it once (nvcc cross-compiles without a
+    # GPU); on the GPU box the prebuilt file that travelled with the snapshot is used as it is
+    from nlp_b200 import build as b
+    if not os.path.exists(b.OUT):
+        b.build()
 
 
 def pytest_collection_modifyitems(config, items):
