@@ -74,7 +74,7 @@ func NewLatentDirichletAllocation(k int) *LatentDirichletAllocation {
 		RhoTheta: LearningSchedule{S: 1, Tau: 10, Kappa: 0.9},
 		rhoPhiT:  1, rhoThetaT: 1,
 		Rnd: rand.New(src), src: src,
-		Processes: 1,
+		Processes: runtime.GOMAXPROCS(0), // lda.go:185
 	}
 	runtime.SetFinalizer(l, (*LatentDirichletAllocation).Close)
 	return l

@@ -106,7 +106,8 @@ typedef struct {
 
 typedef struct lda_b200_handle lda_b200_handle;
 
-/* fills the defaults of NewLatentDirichletAllocation(k), lda.go:145-189 */
+/* fills the defaults of NewLatentDirichletAllocation(k), lda.go:145-189 (processes = the host's hardware threads, as
+ * lda.go:185 takes runtime.GOMAXPROCS(0)) */
 void lda_b200_default_config(int32_t k, lda_b200_config *out);
 
 /* NewLatentDirichletAllocation, lda.go:145: allocates the model on CUDA device `device`. */

@@ -4,11 +4,13 @@
 // argument meaning, result orientation (K x D / K x W) and error behaviour (Transform / FitTransform report errors,
 // Fit / Perplexity / Components have no error slot and throw with the library's "nlp: " prefix).  Header only.
 #pragma once
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lda_b200.h"
@@ -93,7 +95,8 @@ class LatentDirichletAllocation {
     LearningSchedule RhoPhi{10, 1000, 0.9};
     LearningSchedule RhoTheta{1, 10, 0.9};
     rand::Rand Rnd;
-    int Processes = 1;  // minibatches in flight per step (lda.go:134); on one GPU they share a launch
+    // minibatches in flight per step (lda.go:134; default runtime.GOMAXPROCS(0), lda.go:185); on one GPU they share a launch
+    int Processes = (int)std::max(1u, std::thread::hardware_concurrency());
     int Device = 0;     // CUDA device ordinal (not in the reference)
     std::vector<double> PerplexityTrace;  // perplexities evaluated inside the last fit (lda.go:530-539 hides them)
     int IterationsRun = 0;

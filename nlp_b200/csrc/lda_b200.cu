@@ -1380,7 +1380,7 @@ void lda_b200_default_config(int32_t k, lda_b200_config *c) {
     c->transformation_passes = 500;
     c->perplexity_evaluation_frequency = 30;
     c->change_evaluation_frequency = 30;
-    c->processes = 1;
+    c->processes = (int32_t)std::max(1u, std::thread::hardware_concurrency());  // lda.go:185: runtime.GOMAXPROCS(0)
     c->perplexity_tolerance = 1e-2;
     c->mean_change_tolerance = 1e-5;
     c->alpha = 0.1;

@@ -109,8 +109,11 @@ class LatentDirichletAllocation:
         self.w = self.d = 0
         import time
         self.Rnd = rand.New(rand.NewSource(time.time_ns() & 0xFFFFFFFFFFFFFFFF))
-        # Processes (lda.go:134) = number of minibatches in flight = number of GPUs = torch.distributed world size
-        self.Processes = _world()[1]
+        # Processes (lda.go:134) = minibatches in flight per step.  Default as in lda.go:185 -- runtime.GOMAXPROCS(0), the
+        # host's hardware threads -- and at least one per GPU of the torch.distributed job; the GPUs share them
+        # (Processes / GPUs consecutive minibatches per launch, at most 16).  Processes = 1 is the deterministic parity mode.
+        import os
+        self.Processes = max(_world()[1], os.cpu_count() or 1)
         # --- not in the reference ---
         self.Device = device
         self.DeviceInit = True       # draw the initial nPhi / nTheta from Rnd on the GPU (bit-identical stream)

@@ -62,6 +62,7 @@ def test_default_config_matches_reference_defaults():
             continue
         assert getattr(py, f) == getattr(c, f), f
     assert (lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus) == (1.0, 1.0, 0.0)  # lda.go:182-183
+    assert c.processes == lda.Processes == os.cpu_count()                      # lda.go:185: runtime.GOMAXPROCS(0)
 
 
 def test_pcg_matches_oracle_and_known_answers():

@@ -26,6 +26,7 @@ PERP_RTOL = 1e-3
 def new_lda(k, seed=0, **fields):
     lda = nlp_b200.NewLatentDirichletAllocation(k)
     lda.Rnd = rand.New(rand.NewSource(seed))
+    lda.Processes = 1   # the deterministic parity mode (the default is the host's core count, lda.go:185)
     for f, v in fields.items():
         assert hasattr(lda, f), f
         setattr(lda, f, v)

@@ -45,7 +45,8 @@ def _worker(rank, world, port, case, peer, ret):
             indptr, ind, data = np.concatenate(([0], np.cumsum(lens))), ind[sel], data[sel]
         m = CSC(W, D, indptr, ind, data)
         lda = nlp_b200.NewLatentDirichletAllocation(K)
-        assert lda.Device == rank and lda.Processes == world
+        assert lda.Device == rank and lda.Processes >= world
+        lda.Processes = world   # one minibatch per GPU and step: the oracle's SyncGroup = world
         lda.Rnd = rand.New(rand.NewSource(0))
         lda.BatchSize, lda.Iterations = b, iters
         lda.PerplexityEvaluationFrequency, lda.PerplexityTolerance = 1, 0.0
