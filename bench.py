@@ -49,6 +49,8 @@ def parse():
     p.add_argument("--cpu-docs-per-worker", type=int, default=256)
     p.add_argument("--cpu-max-threads", type=int, default=64)
     p.add_argument("--e2e-warmup", type=int, default=1, help="untimed FitTransform calls (1 iteration) before the timed one")
+    p.add_argument("--deterministic", action="store_true",
+                   help="bitwise reproducible fits: fixed-point accumulation of nPhiHat (lda_b200_set_deterministic)")
     p.add_argument("--skip-cpu", action="store_true")
     p.add_argument("--skip-e2e", action="store_true")
     p.add_argument("--skip-parity", action="store_true")
@@ -254,6 +256,7 @@ def ours(args):
         lda.BatchSize = b
         lda.Iterations = iterations
         lda.Processes = world * args.processes_per_gpu
+        lda.Deterministic = args.deterministic
         return lda
 
     B = 1  # BurnInPasses default
@@ -384,7 +387,7 @@ def ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: LDA SCVB0 fit, K=%d, %d docs x %d vocab, %d nnz (Zipfian planted-LDA corpus, seed 12345)"
                        % (cfgname, K, D, W, nnz), "batch_size": b, "processes": world * args.processes_per_gpu,
-                       "burn_in_passes": B,
+                       "burn_in_passes": B, "deterministic": bool(args.deterministic),
                        "parallelism": "dp%d (minibatch m -> GPU m %% %d, %d minibatches per GPU per step, %s)" % (
                            world, world, args.processes_per_gpu, exchange),
                        "step": "one SCVB0 iteration over all %d minibatches (%d launches per GPU)" % (

@@ -55,6 +55,8 @@ type LatentDirichletAllocation struct {
 	Processes int
 	// Device is the CUDA device ordinal (not in the reference).
 	Device int
+	// Deterministic makes fits bitwise reproducible from run to run (not in the reference; lda_b200_set_deterministic).
+	Deterministic bool
 
 	rhoPhiT, rhoThetaT, wordsInCorpus float64 // lda.go:117-120
 	w, d                              int
@@ -110,6 +112,11 @@ func (l *LatentDirichletAllocation) handle() (*C.lda_b200_handle, error) {
 	} else if rc := C.lda_b200_set_config(l.h, &cfg); rc != 0 {
 		return nil, l.err()
 	}
+	det := C.int32_t(0)
+	if l.Deterministic {
+		det = 1
+	}
+	C.lda_b200_set_deterministic(l.h, det)
 	return l.h, nil
 }
 

@@ -232,6 +232,14 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                          float *elapsed_ms);
 int lda_b200_fit_end(lda_b200_handle *h, double *theta_out);
 
+/* Deterministic mode (not in the reference, whose goroutine pool is itself racy for Processes > 1): with on != 0 every
+ * later fit on this handle is bitwise reproducible from run to run for the same inputs, configuration and number of
+ * GPUs.  The sufficient statistics nPhiHat (lda.go:293) are then accumulated as 64-bit fixed-point integers, whose
+ * atomic sums do not depend on the order in which documents finish, and converted to fp32 once per launch; all other
+ * cross-block sums are always taken in a fixed order.  Costs one extra pass over nPhiHat per step and 8-byte instead of
+ * 4-byte reductions.  Off by default: fp32 reductions in arrival order, results equal up to rounding. */
+int lda_b200_set_deterministic(lda_b200_handle *h, int32_t on);
+
 /* per-launch CUDA-event timing of the minibatch / blend kernels on the handle's stream (off by default) */
 int lda_b200_set_profiling(lda_b200_handle *h, int32_t on);
 /* number of kernels launched by this handle since creation (bench.py's gpu_launches) */

@@ -97,6 +97,7 @@ class LatentDirichletAllocation {
     rand::Rand Rnd;
     // minibatches in flight per step (lda.go:134; default runtime.GOMAXPROCS(0), lda.go:185); on one GPU they share a launch
     int Processes = (int)std::max(1u, std::thread::hardware_concurrency());
+    bool Deterministic = false;  // not in the reference: bitwise run-to-run reproducible fits (lda_b200_set_deterministic)
     int Device = 0;     // CUDA device ordinal (not in the reference)
     std::vector<double> PerplexityTrace;  // perplexities evaluated inside the last fit (lda.go:530-539 hides them)
     int IterationsRun = 0;
@@ -223,6 +224,7 @@ class LatentDirichletAllocation {
             err = std::string("nlp: ") + lda_b200_last_error(h_);
             return false;
         }
+        lda_b200_set_deterministic(h_, Deterministic ? 1 : 0);
         return true;
     }
     void fit(const lda_b200_matrix &c, bool want, mat::Dense *theta, std::string &err) {

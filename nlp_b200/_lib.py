@@ -77,6 +77,7 @@ SYMBOLS = {
     "lda_b200_fit_iterate": (C.c_int, [_P, C.c_int32, C.POINTER(Counters), _P, C.c_int32, C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]),
     "lda_b200_fit_end": (C.c_int, [_P, _P]),
+    "lda_b200_set_deterministic": (C.c_int, [_P, C.c_int32]),
     "lda_b200_set_profiling": (C.c_int, [_P, C.c_int32]),
     "lda_b200_launch_count": (C.c_int64, [_P]),
     "lda_b200_last_kernel_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_float),

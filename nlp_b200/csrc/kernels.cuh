@@ -29,6 +29,14 @@ __device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                  : "memory");
 }
+// the same four values into the fixed-point image: x * scale is exact (power of two), the conversion rounds to nearest,
+// and integer addition is associative -- the sum is the same whatever order the reductions land in
+__device__ __forceinline__ void red_add_fx4(unsigned long long *addr, float4 v, float scale) {
+    atomicAdd(addr + 0, (unsigned long long)__float2ll_rn(v.x * scale));
+    atomicAdd(addr + 1, (unsigned long long)__float2ll_rn(v.y * scale));
+    atomicAdd(addr + 2, (unsigned long long)__float2ll_rn(v.z * scale));
+    atomicAdd(addr + 3, (unsigned long long)__float2ll_rn(v.w * scale));
+}
 
 template <int LANES>
 __device__ __forceinline__ float group_sum(float x) {
@@ -65,6 +73,10 @@ struct DocsArgs {
     // MAX_CONCURRENT_MB consecutive local minibatches of mb_docs documents (the reference's `Processes`).
     float hat_scale[16];
     int mb_docs;
+    // deterministic mode: the sufficient statistics are accumulated as 64-bit fixed-point integers (value * fx_scale,
+    // fx_scale a power of two), whose atomic sums do not depend on the order in which the warps arrive
+    unsigned long long *hat_fx;  // [W][Kp]
+    float fx_scale;
 };
 constexpr int MAX_CONCURRENT_MB = 16;
 
@@ -74,7 +86,7 @@ constexpr int MAX_CONCURRENT_MB = 16;
 //   MAIN  (lda.go:292-295):           nPhiHat[i,k] += N gamma_k / batchSize   (no factor v)
 // (1-rho)^v is evaluated once per token by the lane that loads it: q = 1-(1-rho)^v = -expm1(v ln(1-rho)),
 // which keeps full relative accuracy when rho is small (the reference calls math.Pow 2K times per token).
-template <int LANES, int NV, int P, bool MAIN>
+template <int LANES, int NV, int P, bool MAIN, bool DET = false>
 __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int len, int maxlen, float l1m, float wcj,
                                            float hat_scale, int g, float4 (&th)[NV], const bool (&ok)[NV]) {
     for (int tile = 0; tile < maxlen; tile += LANES) {
@@ -140,9 +152,13 @@ __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int 
                             const float sc = hat_scale * r;
 #pragma unroll
                             for (int v = 0; v < NV; ++v)
-                                if (ok[v])
-                                    red_add_v4(a.nphi_hat + (int64_t)w * a.Kp + 4 * (v * LANES + g),
-                                               make_float4(sc * gm[v].x, sc * gm[v].y, sc * gm[v].z, sc * gm[v].w));
+                                if (ok[v]) {
+                                    const float4 add = make_float4(sc * gm[v].x, sc * gm[v].y, sc * gm[v].z, sc * gm[v].w);
+                                    if (DET)
+                                        red_add_fx4(a.hat_fx + (int64_t)w * a.Kp + 4 * (v * LANES + g), add, a.fx_scale);
+                                    else
+                                        red_add_v4(a.nphi_hat + (int64_t)w * a.Kp + 4 * (v * LANES + g), add);
+                                }
                         }
                     }
                 }
@@ -154,7 +170,7 @@ __device__ __forceinline__ void token_pass(const DocsArgs &a, int64_t base, int 
 // Fused SCVB0 kernel: burnInDoc (lda.go:218-261) for `passes` passes with its early exit, then (FIT) the
 // sufficient-statistics pass of fitMiniBatch (lda.go:274-297).  FIT = false is unNormalisedTransform's
 // per-document loop (lda.go:429-435).
-template <int LANES, int NV, int P, bool FIT>
+template <int LANES, int NV, int P, bool FIT, bool DET = false>
 __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
     constexpr int GPW = 32 / LANES;  // documents per warp
     const int lane = threadIdx.x & 31;
@@ -218,7 +234,7 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
         if (FIT) {
             const float l1m = a.log1m_rho[a.passes];  // lda.go:274
             const float hs = valid ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
-            token_pass<LANES, NV, P, true>(a, base, len, maxlen, l1m, wcj, hs, g, th, ok);
+            token_pass<LANES, NV, P, true, DET>(a, base, len, maxlen, l1m, wcj, hs, g, th, ok);
         }
         if (valid) {
 #pragma unroll
@@ -268,7 +284,7 @@ constexpr int docs32_ring_rows(int NV) { return NV == 1 ? 8 : NV == 2 ? 6 : NV =
 constexpr int docs32_min_blocks(int NV) { return NV <= 2 ? 4 : NV == 4 ? 2 : 1; }
 constexpr int docs32_smem_bytes(int NV) { return 8 * docs32_ring_rows(NV) * NV * 512; }
 
-template <int NV, bool FULLK, bool FIT>
+template <int NV, bool FULLK, bool FIT, bool DET = false>
 __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
     constexpr int R = docs32_ring_rows(NV);
     extern __shared__ float4 ring_all[];
@@ -405,12 +421,17 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                 if (MAINP) {
                     const int w = __shfl_sync(FULL, cur.wi, t);
                     const float sc = hat_scale * r;
-                    float *hp = reinterpret_cast<float *>(reinterpret_cast<char *>(a.nphi_hat) + (size_t)((unsigned)w * row_vecs + lane_vec) * 16u);
+                    const size_t hoff = (size_t)((unsigned)w * row_vecs + lane_vec) * 4u;  // in elements
 #pragma unroll
                     for (int v = 0; v < NV; ++v)
-                        if (ok[v])
-                            red_add_v4(hp + 128 * v, make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y,
-                                                                 sc * c[v].z * tha[v].z, sc * c[v].w * tha[v].w));
+                        if (ok[v]) {
+                            const float4 add = make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y, sc * c[v].z * tha[v].z,
+                                                           sc * c[v].w * tha[v].w);
+                            if (DET)
+                                red_add_fx4(a.hat_fx + hoff + 128 * v, add, a.fx_scale);
+                            else
+                                red_add_v4(a.nphi_hat + hoff + 128 * v, add);
+                        }
                 }
 #pragma unroll
                 for (int v = 0; v < NV; ++v) {
@@ -464,10 +485,31 @@ __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, 
 
 // M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58), as three launches on the stream:
 //   hat_colsum_kernel : nZHat[k] = sum_w nPhiHat[w,k]   (== the reference's running sum, lda.go:295)
-//   nz_update_kernel  : nZ = A nZ + C nZHat ; invZ = 1/(nZ + eta W) ; scheduler reset              (lda.go:313-317)
+//   nz_update_kernel  : nZHat = sum of the per-block sums ; nZ = A nZ + C nZHat ; invZ = 1/(nZ + eta W) ; scheduler reset (lda.go:313-317)
 //   phi_blend_kernel  : nPhi = A nPhi + C nPhiHat ; nPhiHat = 0 ; c = (nPhi + eta) invZ            (lda.go:303-310)
 // blockDim.x = VPR*RPB with VPR = Kp/4 float4 per row, so a thread always owns the same 4 topics.
-__global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64_t W, int Kp, double *nzhat) {
+// Cross-block sums (column sums, perplexity, word counts) are taken in two steps so that they do not depend on the order
+// in which blocks finish: every block stores its partial result, sum_partials_kernel adds the blocks in index order.
+__global__ void sum_partials_kernel(const double *partials, int nblocks, int n, double *out, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * n + i];
+    out[i] = accumulate ? out[i] + s : s;
+}
+
+// fixed-point sufficient statistics -> fp32 nPhiHat (deterministic mode), and the fixed-point image back to zero
+__global__ void hat_fx_to_float_kernel(unsigned long long *fx, float *hat, int64_t n, double inv_scale) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long q = (long long)fx[i];
+        if (q != 0) {
+            hat[i] = (float)((double)q * inv_scale);
+            fx[i] = 0ull;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64_t W, int Kp, double *partials) {
     extern __shared__ float4 sm4[];
     const int VPR = Kp >> 2;
     const int RPB = blockDim.x / VPR;
@@ -492,24 +534,40 @@ __global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64
             sz += t.z;
             sw += t.w;
         }
-        atomicAdd(nzhat + 4 * col + 0, sx);
-        atomicAdd(nzhat + 4 * col + 1, sy);
-        atomicAdd(nzhat + 4 * col + 2, sz);
-        atomicAdd(nzhat + 4 * col + 3, sw);
+        double *p = partials + (size_t)blockIdx.x * Kp + 4 * col;
+        p[0] = sx;
+        p[1] = sy;
+        p[2] = sz;
+        p[3] = sw;
     }
 }
 
-__global__ void nz_update_kernel(double *nz, double *nzhat, float *inv_z, int *doc_counter, int K, int Kp, double Ad,
-                                 double Cd, double etaW) {
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+// launched as one block of 1024 threads: four threads share a topic, each adds every fourth block's partial sum (eight
+// loads in flight), and the four shares are combined in a fixed order -- the result does not depend on timing
+__global__ void __launch_bounds__(1024) nz_update_kernel(double *nz, const double *partials, int nblocks, float *inv_z, int *doc_counter,
+                                                         int K, int Kp, double Ad, double Cd, double etaW) {
+    __shared__ double share[4][256];
+    const int lane_k = threadIdx.x & 255, part = threadIdx.x >> 8;
+    for (int k0 = 0; k0 < Kp; k0 += 256) {
+        const int k = k0 + lane_k;
+        double s = 0;
         if (k < K) {
-            const double z = Ad * nz[k] + Cd * nzhat[k];
-            nz[k] = z;
-            inv_z[k] = (float)(1.0 / (z + etaW));
-        } else {
-            inv_z[k] = 0.f;
+#pragma unroll 8
+            for (int b = part; b < nblocks; b += 4) s += partials[(size_t)b * Kp + k];
         }
-        nzhat[k] = 0.0;
+        share[part][lane_k] = s;
+        __syncthreads();
+        if (part == 0 && k < Kp) {
+            if (k < K) {
+                const double zhat = ((share[0][lane_k] + share[1][lane_k]) + share[2][lane_k]) + share[3][lane_k];  // nZHat[k]
+                const double z = Ad * nz[k] + Cd * zhat;
+                nz[k] = z;
+                inv_z[k] = (float)(1.0 / (z + etaW));
+            } else {
+                inv_z[k] = 0.f;
+            }
+        }
+        __syncthreads();
     }
     if (threadIdx.x == 0) *doc_counter = 0;
 }
@@ -571,7 +629,7 @@ struct FusedArgs {
     int64_t row0, row1, W;
     int Kp;
     float A, C;
-    double *nzhat_local;     // [Kp] this rank's partial column sums (zero on entry)
+    double *partials;        // [gridDim.x][Kp] per-block column sums of this rank's slice (summed in block order afterwards)
 };
 
 // U rows per thread and iteration: with few ranks a thread has few peer loads of its own, and U independent rows keep
@@ -647,10 +705,11 @@ __global__ void __launch_bounds__(256) peer_reduce_blend_kernel(const FusedArgs 
             sz += t.z;
             sw += t.w;
         }
-        atomicAdd(a.nzhat_local + 4 * col + 0, sx);
-        atomicAdd(a.nzhat_local + 4 * col + 1, sy);
-        atomicAdd(a.nzhat_local + 4 * col + 2, sz);
-        atomicAdd(a.nzhat_local + 4 * col + 3, sw);
+        double *p = a.partials + (size_t)blockIdx.x * a.Kp + 4 * col;
+        p[0] = sx;
+        p[1] = sy;
+        p[2] = sz;
+        p[3] = sw;
     }
 }
 
@@ -729,8 +788,8 @@ __global__ void inv_z_kernel(const double *nz, float *inv_z, int K, int Kp, doub
 }
 
 // column sums over rows of a [R][Kp] fp32 matrix into double[Kp] (normalisePhi's sum, lda.go:351-356; init's
-// nZ, lda.go:203).  out must be zero on entry.  Same thread->column mapping as phi_blend_kernel.
-__global__ void __launch_bounds__(256) colsum_kernel(const float *src, int64_t R, int Kp, double *out) {
+// nZ, lda.go:203) as per-block partials [gridDim.x][Kp] (see sum_partials_kernel).  Same thread->column mapping as phi_blend_kernel.
+__global__ void __launch_bounds__(256) colsum_kernel(const float *src, int64_t R, int Kp, double *partials) {
     extern __shared__ float4 sm4[];
     const int VPR = Kp >> 2;
     const int RPB = blockDim.x / VPR;
@@ -754,7 +813,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float *src, int64_t R
         for (int c = 0; c < 4; ++c) {
             double s = 0;
             for (int q = 0; q < RPB; ++q) s += smd[4 * (q * VPR + col) + c];
-            atomicAdd(out + 4 * col + c, s);
+            partials[(size_t)blockIdx.x * Kp + 4 * col + c] = s;
         }
     }
 }
@@ -773,7 +832,7 @@ struct PerpArgs {
     const float *theta;
     const float *nphi;
     const float *inv_colsum;  // [Kp], 0 on the pad
-    double *acc;              // scalar
+    double *partials;         // [gridDim.x] per-block sums
     int n_docs;
     int Kp;
 };
@@ -861,7 +920,7 @@ __global__ void __launch_bounds__(256) perplexity_kernel(const PerpArgs a) {
     if (threadIdx.x == 0) {
         double s = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
-        atomicAdd(a.acc, s);
+        a.partials[blockIdx.x] = s;
     }
 }
 
@@ -1000,9 +1059,10 @@ __global__ void dense_col_fill_kernel(const double *a, int64_t W, int64_t D, con
     }
 }
 
-// wc[j] = sum of the document's values (lda.go:476-480), float64 accumulation; *n_total += sum_j wc[j] (lda.go:481)
+// wc[j] = sum of the document's values (lda.go:476-480), float64 accumulation; partials[block] = the block's share of
+// sum_j wc[j] (lda.go:481)
 __global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, const float *val, int n_docs, float *wc,
-                                                     double *wc64, double *n_total) {
+                                                     double *wc64, double *partials) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const int nwarps = (gridDim.x * blockDim.x) >> 5;
     double tot = 0;
@@ -1024,7 +1084,7 @@ __global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, con
     if (threadIdx.x == 0) {
         double s = 0;
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
-        if (s != 0) atomicAdd(n_total, s);
+        partials[blockIdx.x] = s;
     }
 }
 

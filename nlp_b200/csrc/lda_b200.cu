@@ -110,6 +110,10 @@ struct lda_b200_handle {
     double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
     float *rho_tab = nullptr;
     int rho_cap = 0;
+    double *partials = nullptr;  // per-block partial sums of the cross-block reductions (summed in block order)
+    size_t partials_cap = 0;
+    bool deterministic = false;  // sufficient statistics accumulated in 64-bit fixed point (lda_b200_set_deterministic)
+    unsigned long long *hat_fx = nullptr;
     void *stage = nullptr;
     size_t stage_bytes = 0;
     double *h_pinned = nullptr;  // small pinned read-back area
@@ -266,6 +270,19 @@ inline int grid_for(int64_t n, int threads, int cap) {
     return (int)std::min<int64_t>(g, cap);
 }
 
+// out[0..n) (+)= sum over the nblocks per-block partials written by the kernel just launched on st, in block order
+int ensure_partials(lda_b200_handle *h, size_t doubles) {
+    if (doubles <= h->partials_cap) return 0;
+    TRY(dalloc(h, &h->partials, doubles));
+    h->partials_cap = doubles;
+    return 0;
+}
+int reduce_partials(lda_b200_handle *h, int nblocks, int n, double *out, bool accumulate, cudaStream_t st) {
+    sum_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(h->partials, nblocks, n, out, accumulate ? 1 : 0);
+    KCHECK();
+    return 0;
+}
+
 int validate_config(lda_b200_handle *h, const lda_b200_config *c) {
     if (!c) return fail(h, LDA_B200_EINVAL, "config is NULL");
     if (c->K < 1) return fail(h, LDA_B200_EINVAL, "K must be >= 1 (got %d)", c->K);
@@ -311,19 +328,35 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
         KCHECK();
         return 0;
     };
-    if (vecs <= 4) return narrow(scvb0_docs_kernel<4, 1, 4, FIT>, 4);
-    if (vecs <= 8) return narrow(scvb0_docs_kernel<8, 1, 4, FIT>, 8);
-    if (vecs <= 16) return narrow(scvb0_docs_kernel<16, 1, 4, FIT>, 16);
-    if (vecs < 32) return wide(scvb0_docs32_kernel<1, false, FIT>, 1);
-    if (vecs == 32) return wide(scvb0_docs32_kernel<1, true, FIT>, 1);
-    if (vecs < 64) return wide(scvb0_docs32_kernel<2, false, FIT>, 2);
-    if (vecs == 64) return wide(scvb0_docs32_kernel<2, true, FIT>, 2);
-    if (vecs < 128) return wide(scvb0_docs32_kernel<4, false, FIT>, 4);
-    if (vecs == 128) return wide(scvb0_docs32_kernel<4, true, FIT>, 4);
-    if (vecs < 256) return wide(scvb0_docs32_kernel<8, false, FIT>, 8);
-    return wide(scvb0_docs32_kernel<8, true, FIT>, 8);
+    // deterministic mode (fit only): the variants that accumulate the sufficient statistics in fixed point
+    constexpr bool CAN_DET = FIT;
+    const bool det = CAN_DET && a.hat_fx != nullptr;
+#define LDA_NARROW(L)                                                              \
+    do {                                                                           \
+        if (det) return narrow(scvb0_docs_kernel<L, 1, 4, FIT, CAN_DET>, L);       \
+        return narrow(scvb0_docs_kernel<L, 1, 4, FIT, false>, L);                  \
+    } while (0)
+#define LDA_WIDE(NV, FULLK)                                                        \
+    do {                                                                           \
+        if (det) return wide(scvb0_docs32_kernel<NV, FULLK, FIT, CAN_DET>, NV);    \
+        return wide(scvb0_docs32_kernel<NV, FULLK, FIT, false>, NV);               \
+    } while (0)
+    if (vecs <= 4) LDA_NARROW(4);
+    if (vecs <= 8) LDA_NARROW(8);
+    if (vecs <= 16) LDA_NARROW(16);
+    if (vecs < 32) LDA_WIDE(1, false);
+    if (vecs == 32) LDA_WIDE(1, true);
+    if (vecs < 64) LDA_WIDE(2, false);
+    if (vecs == 64) LDA_WIDE(2, true);
+    if (vecs < 128) LDA_WIDE(4, false);
+    if (vecs == 128) LDA_WIDE(4, true);
+    if (vecs < 256) LDA_WIDE(8, false);
+    LDA_WIDE(8, true);
+#undef LDA_NARROW
+#undef LDA_WIDE
 }
 
+// sum over the documents' entries of log2(dot) * v into h->dacc[0]
 int launch_perplexity(lda_b200_handle *h, const PerpArgs &a) {
     const int vecs = a.Kp / 4;
     if (a.n_docs <= 0) return 0;
@@ -331,9 +364,12 @@ int launch_perplexity(lda_b200_handle *h, const PerpArgs &a) {
         const int gpw = 32 / lanes;
         const int64_t warps = ((int64_t)a.n_docs + gpw - 1) / gpw;
         const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * 8);
-        kern<<<grid, 256, 0, h->stream>>>(a);
+        TRY(ensure_partials(h, (size_t)grid));
+        PerpArgs b = a;
+        b.partials = h->partials;
+        kern<<<grid, 256, 0, h->stream>>>(b);
         KCHECK();
-        return 0;
+        return reduce_partials(h, grid, 1, h->dacc, false, h->stream);
     };
     if (vecs <= 4) return go(perplexity_kernel<4, 1, 4>, 4);
     if (vecs <= 8) return go(perplexity_kernel<8, 1, 4>, 8);
@@ -575,13 +611,15 @@ int fill_rho_table(lda_b200_handle *h, double t0, int n) {
 }
 
 // nZ[k] = sum_i nPhi[i,k] (lda.go:203) and invZ
-int refresh_nz_from_nphi(lda_b200_handle *h) {
-    CU(cudaMemsetAsync(h->nz, 0, (size_t)h->Kp * sizeof(double), h->stream));
-    const int bs = blend_block(h->Kp);
-    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->nz);
+// out[k] = sum_w src[w,k] over the W x Kp matrix src, float64, blocks added in index order
+int column_sums(lda_b200_handle *h, const float *src, double *out) {
+    const int bs = blend_block(h->Kp), grid = h->sms * 2;
+    TRY(ensure_partials(h, (size_t)grid * h->Kp));
+    colsum_kernel<<<grid, bs, (size_t)bs * 32, h->stream>>>(src, h->W, h->Kp, h->partials);
     KCHECK();
-    return 0;
+    return reduce_partials(h, grid, h->Kp, out, false, h->stream);
 }
+int refresh_nz_from_nphi(lda_b200_handle *h) { return column_sums(h, h->nphi, h->nz); }
 // invZ from nZ and c = (nPhi + eta) invZ from nPhi (after init / set_state / a change of Eta)
 int refresh_inv_z(lda_b200_handle *h) {
     inv_z_kernel<<<(h->Kp + 127) / 128, 128, 0, h->stream>>>(h->nz, h->inv_z, h->K, h->Kp, h->cfg.eta * (double)h->W);
@@ -753,6 +791,15 @@ int upload_rows(lda_b200_handle *h, const std::vector<Segment> &segs, const doub
     return 0;
 }
 
+// wc of the local documents [la, lb) (lda.go:476-480) and their share of the corpus total added to h->dacc[1] (lda.go:481)
+int doc_word_counts(lda_b200_handle *h, Corpus &c, int64_t la, int64_t lb, double *wc64_out, cudaStream_t st) {
+    const int grid = grid_for((lb - la) * 32, 256, h->sms * 8);
+    TRY(ensure_partials(h, (size_t)grid));
+    doc_wc_kernel<<<grid, 256, 0, st>>>(c.doc_ptr + la, c.val, (int)(lb - la), c.wc + la, wc64_out ? wc64_out + la : nullptr, h->partials);
+    KCHECK();
+    return reduce_partials(h, grid, 1, h->dacc + 1, true, st);
+}
+
 // Entries of the local documents [la, lb) -> c.val / c.ind on stream st: the caller's slices of the owning segments go
 // through the stage buffer (host sources) or are read in place (device sources); values float64 -> fp32, word ids
 // int64 -> int32 with the range check of narrow_ind_kernel.
@@ -860,10 +907,7 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     }
     pt.lap("ingest: H2D + narrow + length sort");
     if (streamed) return 0;
-    if (Dl > 0) {
-        doc_wc_kernel<<<grid_for(Dl * 32, 256, h->sms * 8), 256, 0, h->stream>>>(c.doc_ptr, c.val, (int)Dl, c.wc, wc64_out, h->dacc + 1);
-        KCHECK();
-    }
+    if (Dl > 0) TRY(doc_word_counts(h, c, 0, Dl, wc64_out, h->stream));
     if (h->nranks > 1) NC(nccl().AllReduce(h->dacc + 1, h->dacc + 1, 1, ncclDouble, ncclSum, h->comm, h->stream));
     CU(cudaMemcpyAsync(h->h_pinned, h->dacc + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(h->h_pinned + 1, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
@@ -917,10 +961,7 @@ void advance(lda_b200_pcg *rnd, uint64_t draws) {
 // perplexity (lda.go:392-408) of the corpus under theta and the current nPhi, with denominator `sum`
 int eval_perplexity(lda_b200_handle *h, const Corpus &c, double sum, double *out) {
     Nvtx range("lda_b200: perplexity");
-    CU(cudaMemsetAsync(h->colsum, 0, (size_t)h->Kp * sizeof(double), h->stream));
-    const int bs = blend_block(h->Kp);
-    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->colsum);
-    KCHECK();
+    TRY(column_sums(h, h->nphi, h->colsum));
     reciprocal_kernel<<<(h->Kp + 127) / 128, 128, 0, h->stream>>>(h->colsum, h->inv_colsum, h->K, h->Kp);
     KCHECK();
     CU(cudaMemsetAsync(h->dacc, 0, sizeof(double), h->stream));
@@ -931,7 +972,7 @@ int eval_perplexity(lda_b200_handle *h, const Corpus &c, double sum, double *out
     a.theta = c.theta;
     a.nphi = h->nphi;
     a.inv_colsum = h->inv_colsum;
-    a.acc = h->dacc;
+    a.partials = nullptr;  // set by launch_perplexity
     a.n_docs = (int)c.Dl;
     a.Kp = h->Kp;
     TRY(launch_perplexity(h, a));
@@ -1012,6 +1053,8 @@ DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
     a.eta = (float)h->cfg.eta;
     for (float &x : a.hat_scale) x = 0.f;
     a.mb_docs = (int)std::max<int64_t>(1, c.b);
+    a.hat_fx = nullptr;
+    a.fx_scale = 1.f;
     return a;
 }
 
@@ -1119,11 +1162,7 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *the
             } else if (streamed) {
                 TRY(upload_part(h, c, la, lb, cs, true, true));  // device source: read in place
             }
-            if (streamed) {
-                doc_wc_kernel<<<grid_for((lb - la) * 32, 256, h->sms * 8), 256, 0, cs>>>(c.doc_ptr + la, c.val, (int)(lb - la), c.wc + la,
-                                                                                              nullptr, h->dacc + 1);
-                KCHECK();
-            }
+            if (streamed) TRY(doc_word_counts(h, c, la, lb, nullptr, cs));
             CU(cudaMemsetAsync(a.doc_counter, 0, sizeof(int), cs));
             a.doc_begin = (int)la;
             a.doc_end = (int)lb;
@@ -1459,6 +1498,8 @@ void lda_b200_destroy(lda_b200_handle *h) {
     dfree(h, &h->err_flag);
     dfree(h, &h->dacc);
     dfree(h, &h->rho_tab);
+    dfree(h, &h->partials);
+    dfree(h, &h->hat_fx);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->stage) cudaFree(h->stage);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1487,6 +1528,13 @@ int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg) {
         CU(cudaSetDevice(h->device));
         TRY(refresh_inv_z(h));  // invZ and c = (nPhi + eta) invZ depend on Eta
     }
+    return 0;
+}
+
+int lda_b200_set_deterministic(lda_b200_handle *h, int32_t on) {
+    if (!h) return LDA_B200_EINVAL;
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    h->deterministic = on != 0;
     return 0;
 }
 
@@ -1562,6 +1610,12 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
         CU(cudaMemsetAsync(h->hat_buf[1], 0, (size_t)W * h->Kp * sizeof(float), h->stream));
     }
     CU(cudaMemsetAsync(h->nzhat, 0, (size_t)h->Kp * sizeof(double), h->stream));
+    if (h->deterministic) {
+        TRY(dalloc(h, &h->hat_fx, (size_t)W * h->Kp));
+        CU(cudaMemsetAsync(h->hat_fx, 0, (size_t)W * h->Kp * sizeof(unsigned long long), h->stream));
+    } else {
+        dfree(h, &h->hat_fx);
+    }
     uint64_t draws = 0;
     if (warm) {
         // streaming step: nPhi / nZ / rhoPhiT carry over
@@ -1704,7 +1758,24 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 if (c.ind_deferred) CU(cudaStreamWaitEvent(h->stream, c.range_ev[(size_t)(l_first / c.conc)], 0));
                 int slot;
                 TRY(ev_begin(h, 0, &slot));
+                double inv_fx = 1.0;
+                if (h->hat_fx) {
+                    // a word receives at most one contribution of at most hat_scale per document of the launch, so the
+                    // sums stay below hat_scale_max * documents; 2^e is the largest power of two that keeps them < 2^62
+                    float smax = 0.f;
+                    for (float x : a.hat_scale) smax = std::max(smax, fabsf(x));
+                    const double bound = std::max(1.0, (double)smax * (double)(a.doc_end - a.doc_begin));
+                    const int e = std::max(-100, std::min(100, 61 - (int)ceil(log2(bound))));
+                    a.hat_fx = h->hat_fx;
+                    a.fx_scale = (float)ldexp(1.0, e);
+                    inv_fx = ldexp(1.0, -e);
+                }
                 TRY(launch_docs<true>(h, a, c.order));
+                if (h->hat_fx) {
+                    const int64_t n = h->W * h->Kp;
+                    hat_fx_to_float_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>(h->hat_fx, h->nphi_hat, n, inv_fx);
+                    KCHECK();
+                }
                 TRY(ev_end(h, slot));
                 if (stream_out) TRY(stream_theta_range(h, c, a.doc_begin, a.doc_end));
             }
@@ -1740,7 +1811,8 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 fa.Kp = h->Kp;
                 fa.A = (float)Ad;
                 fa.C = (float)Cd;
-                fa.nzhat_local = h->nzhat;
+                TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
+                fa.partials = h->partials;
                 const int bs = blend_block(h->Kp);
                 if (R <= 2)
                     peer_reduce_blend_kernel<4, 2><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
@@ -1749,6 +1821,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 else
                     peer_reduce_blend_kernel<1, 8><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 KCHECK();
+                TRY(reduce_partials(h, h->sms * 4, h->Kp, h->nzhat, false, h->stream));  // this rank's share of nZHat
                 bar.finish = 1;
                 bar.epoch = ++h->epoch;
                 xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
@@ -1778,9 +1851,10 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 const int bs = blend_block(h->Kp);
                 int slot;
                 TRY(ev_begin(h, 1, &slot));
-                hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->nzhat);
+                TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
+                hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->partials);
                 KCHECK();
-                nz_update_kernel<<<1, 256, 0, h->stream>>>(h->nz, h->nzhat, h->inv_z, h->doc_counter, h->K, h->Kp, Ad, Cd,
+                nz_update_kernel<<<1, 1024, 0, h->stream>>>(h->nz, h->partials, h->sms * 4, h->inv_z, h->doc_counter, h->K, h->Kp, Ad, Cd,
                                                            cfg.eta * (double)h->W);
                 KCHECK();
                 BlendArgs ba;
@@ -1987,10 +2061,7 @@ int lda_b200_components(lda_b200_handle *h, double *out) {
     if (!out) return fail(h, LDA_B200_EINVAL, "out is NULL");
     if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Components called before Fit / set_state");
     CU(cudaSetDevice(h->device));
-    CU(cudaMemsetAsync(h->colsum, 0, (size_t)h->Kp * sizeof(double), h->stream));
-    const int bs = blend_block(h->Kp);
-    colsum_kernel<<<h->sms * 2, bs, (size_t)bs * 32, h->stream>>>(h->nphi, h->W, h->Kp, h->colsum);
-    KCHECK();
+    TRY(column_sums(h, h->nphi, h->colsum));
     double *dout = nullptr;
     TRY(dalloc(h, &dout, (size_t)h->K * h->W));
     transpose_out_kernel<false><<<(unsigned)((h->W + 31) / 32), 256, 0, h->stream>>>(h->nphi, h->W, h->K, h->Kp, h->colsum, dout, h->W);

@@ -118,6 +118,7 @@ class LatentDirichletAllocation:
         self.Device = device
         self.DeviceInit = True       # draw the initial nPhi / nTheta from Rnd on the GPU (bit-identical stream)
         self.DeviceConvert = True    # CSR -> CSC (ToCSC, lda.go:464-466) and the dense scan (utils.go:51-57) on the GPU
+        self.Deterministic = False   # bitwise run-to-run reproducible fits (fixed-point nPhiHat, lda_b200_set_deterministic)
         self.PerplexityTrace = []    # perplexities evaluated inside the last fit (lda.go:530-539 hides them)
         self.IterationsRun = 0
         self._h = None
@@ -150,6 +151,9 @@ class LatentDirichletAllocation:
             self._h = h
         else:
             _lib.check(L.lda_b200_set_config(self._h, cfg), self._h)
+        if getattr(self, "_det_set", None) != bool(self.Deterministic):
+            _lib.check(L.lda_b200_set_deterministic(self._h, 1 if self.Deterministic else 0), self._h)
+            self._det_set = bool(self.Deterministic)
         want = max(1, min(self.Processes, _world()[1]))
         if want != self._comm_ranks:
             self._init_comm(want)

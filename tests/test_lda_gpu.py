@@ -102,12 +102,12 @@ def synth(D, W, mean_distinct, block=100, seed=12345):
     return CSC(W, D, indptr, ind, data)
 
 
-def run_pair(m, k, iters, seed=0, theta_atol=THETA_ATOL, **fields):
+def run_pair(m, k, iters, seed=0, theta_atol=THETA_ATOL, cuda_only=None, **fields):
     f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=iters)
     f.update(fields)
     o = new_oracle(k, seed=seed, **f)
     want = o.FitTransform(tuple(m))
-    lda = new_lda(k, seed=seed, **f)
+    lda = new_lda(k, seed=seed, **dict(f, **(cuda_only or {})))
     got = lda.FitTransform(m)
     np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
     assert np.abs(got - want).max() <= theta_atol
@@ -616,6 +616,33 @@ def test_transform_pipeline_ranges(k):
     # Perplexity runs the same pipeline without reading theta back
     p1 = lda.Perplexity(held, theta0=theta0)
     assert np.isfinite(p1) and p1 > 1
+
+
+def test_deterministic_mode_is_bitwise_reproducible():
+    """lda_b200_set_deterministic: fixed-point accumulation of nPhiHat + block-ordered reductions.  Many warps reduce
+    into the same hot rows concurrently (Zipf head, 4 minibatches per launch), the setting in which the default fp32
+    reductions land in a different order from run to run."""
+    indptr, ind, data = corpus_synth.generate(6000, 20000, block=1024, mean_distinct=120)
+    m = CSC(20000, 6000, indptr, ind, data)
+    f = dict(Iterations=6, BatchSize=1024, Processes=4, PerplexityEvaluationFrequency=2, PerplexityTolerance=0.0)
+    runs = []
+    for _ in range(3):
+        lda = new_lda(100, Deterministic=True, **f)
+        theta = lda.FitTransform(m)
+        nphi, nz = lda.GetState()
+        runs.append((theta, nphi, nz, list(lda.PerplexityTrace), lda.Transform(m), lda.Components()))
+        lda.Close()
+    for other in runs[1:]:
+        for a, b in zip(runs[0], other):
+            assert np.array_equal(np.asarray(a), np.asarray(b))
+    # the mode changes rounding only: same results as the default mode and as the oracle within the stated tolerances
+    plain = new_lda(100, **f)
+    theta_plain = plain.FitTransform(m)
+    assert np.abs(theta_plain - runs[0][0]).max() <= THETA_ATOL
+    np.testing.assert_allclose(plain.PerplexityTrace, runs[0][3], rtol=PERP_RTOL)
+    for k, b in ((7, 16), (100, 64), (300, 32)):
+        small = synth(150, 500, 30)
+        run_pair(small, k, 4, BatchSize=b, cuda_only=dict(Deterministic=True))
 
 
 def _full_size_properties(name, batch, processes, iters):
