@@ -490,12 +490,27 @@ __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, 
 // blockDim.x = VPR*RPB with VPR = Kp/4 float4 per row, so a thread always owns the same 4 topics.
 // Cross-block sums (column sums, perplexity, word counts) are taken in two steps so that they do not depend on the order
 // in which blocks finish: every block stores its partial result, sum_partials_kernel adds the blocks in index order.
-__global__ void sum_partials_kernel(const double *partials, int nblocks, int n, double *out, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// One block of 1024 threads per 256 outputs: PARTS threads share an output, each adds every PARTS-th block's partial
+// (independent loads, so several are in flight), and the shares are combined by a fixed tree.  PARTS = 4 for vectors
+// of outputs (column sums), 1024 for a single output (perplexity, word count).
+template <int PARTS>
+__global__ void __launch_bounds__(1024) sum_partials_kernel(const double *partials, int nblocks, int n, double *out, int accumulate) {
+    constexpr int COLS = 1024 / PARTS;
+    __shared__ double share[1024];
+    const int col = threadIdx.x % COLS, part = threadIdx.x / COLS;
+    const int i = blockIdx.x * COLS + col;
     double s = 0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * n + i];
-    out[i] = accumulate ? out[i] + s : s;
+    if (i < n) {
+#pragma unroll 8
+        for (int b = part; b < nblocks; b += PARTS) s += partials[(size_t)b * n + i];
+    }
+    share[part * COLS + col] = s;
+    __syncthreads();
+    for (int half = PARTS / 2; half > 0; half >>= 1) {
+        if (part < half) share[part * COLS + col] += share[(part + half) * COLS + col];
+        __syncthreads();
+    }
+    if (part == 0 && i < n) out[i] = accumulate ? out[i] + share[col] : share[col];
 }
 
 // fixed-point sufficient statistics -> fp32 nPhiHat (deterministic mode), and the fixed-point image back to zero

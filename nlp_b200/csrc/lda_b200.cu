@@ -278,7 +278,10 @@ int ensure_partials(lda_b200_handle *h, size_t doubles) {
     return 0;
 }
 int reduce_partials(lda_b200_handle *h, int nblocks, int n, double *out, bool accumulate, cudaStream_t st) {
-    sum_partials_kernel<<<(n + 127) / 128, 128, 0, st>>>(h->partials, nblocks, n, out, accumulate ? 1 : 0);
+    if (n == 1)
+        sum_partials_kernel<1024><<<1, 1024, 0, st>>>(h->partials, nblocks, n, out, accumulate ? 1 : 0);
+    else
+        sum_partials_kernel<4><<<(n + 255) / 256, 1024, 0, st>>>(h->partials, nblocks, n, out, accumulate ? 1 : 0);
     KCHECK();
     return 0;
 }
