@@ -211,3 +211,39 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in j, key
     assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["value"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_matrix_descriptors_keep_the_callers_storage():
+    """as_matrix hands CSR / CSC / dense inputs to the library in the storage they already have (lda_b200_matrix); other
+    sparse formats and DeviceConvert = False go through the host-side ToCSC restatement (as_csc)"""
+    import scipy.sparse as sp
+    from nlp_b200.lda import CSR, as_matrix
+    a = np.array([[0.0, 2.0, 0.0], [1.0, 0.0, 3.0]])
+    want = as_csc(a)
+    d, rows, cols, keep = as_matrix(a)
+    assert (d.format, rows, cols, d.rows, d.cols) == (_lib.FORMAT_DENSE, 2, 3, 2, 3) and d.ptr is None and d.data == keep[0].ctypes.data
+    d, rows, cols, keep = as_matrix(sp.csr_matrix(a))
+    assert d.format == _lib.FORMAT_CSR and keep[0].tolist() == [0, 1, 3] and keep[1].tolist() == [1, 0, 2]
+    d, _, _, keep = as_matrix(CSR(2, 3, np.array([0, 1, 3]), np.array([1, 0, 2]), np.array([2.0, 1.0, 3.0])))
+    assert d.format == _lib.FORMAT_CSR and keep[2].dtype == np.float64 and keep[0].dtype == np.int64
+    for m in (sp.csc_matrix(a), want, sp.coo_matrix(a), sp.dok_matrix(a)):
+        d, _, _, keep = as_matrix(m)
+        assert d.format == _lib.FORMAT_CSC
+        assert keep[0].tolist() == want.indptr.tolist() and keep[1].tolist() == want.ind.tolist() and keep[2].tolist() == want.data.tolist()
+    d, _, _, keep = as_matrix(sp.csr_matrix(a), device_convert=False)
+    assert d.format == _lib.FORMAT_CSC and keep[1].tolist() == want.ind.tolist()
+    with pytest.raises(ValueError):
+        as_matrix(np.zeros(3))
+
+
+def test_pairwise_comparers_name_the_reference_functions():
+    # measures/pairwise/comparisons.go: nine comparers; the codes are the lda_b200_comparer enum of the header
+    from nlp_b200.measures import pairwise
+    text = open(os.path.join(ROOT, "include", "lda_b200_index.h")).read()
+    enum = dict(re.findall(r"LDA_B200_([A-Z_]+) = (\d+)", text))
+    assert len(pairwise.ALL) == 9
+    for c in pairwise.ALL:
+        snake = re.sub(r"(?<!^)(?=[A-Z])", "_", c.name).upper()
+        assert int(enum[snake]) == c.code, c.name
+    with pytest.raises(TypeError):
+        nlp_b200.NewLinearScanIndex(lambda a, b: 0.0)
