@@ -17,6 +17,8 @@
 
 #include <stdint.h>
 
+#include "lda_b200.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -45,6 +47,14 @@ const char *lda_b200_index_last_error(const lda_b200_index *ix);
 /* Index(v, id), index.go:79-84, for n vectors: column j of m gets ids[j] (ids == NULL: the vector's position, i.e.
  * consecutive numbers continuing from Len()). */
 int lda_b200_index_add(lda_b200_index *ix, int32_t dim, int64_t n, const double *m, int64_t ld, const int64_t *ids);
+
+/* `ColDo(theta, func(j, v) { index.Index(v, ids[j]) })` with theta = lda.Transform(m) (lda.go:446-453), fused: the
+ * Transform pipeline writes the doc-topic vectors of m's documents straight into the index's matrix in HBM, so no vector
+ * crosses the host.  Arguments as lda_b200_transform_matrix; document j of m is indexed under ids[j], or under j when
+ * ids is NULL.  h and ix must live on the same device.  With a communicator every rank indexes the documents of its own
+ * minibatches (a sharded index: search every rank's index and merge). */
+int lda_b200_transform_into_index(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                                  double rho_theta_t, lda_b200_index *ix, const int64_t *ids);
 
 /* Remove(id), index.go:117-135: drops the first vector indexed under id, keeping the order of the others; unknown ids
  * are ignored. */

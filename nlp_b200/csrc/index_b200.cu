@@ -16,6 +16,7 @@
 
 #include "../../include/lda_b200.h"
 #include "../../include/lda_b200_index.h"
+#include "index_internal.h"
 #include "index_kernels.cuh"
 
 using namespace idxb;
@@ -270,6 +271,35 @@ int search_batch(lda_b200_index *ix, const double *d_q, int nb, int k, int64_t *
 }
 
 }  // namespace
+
+int index_begin_append(lda_b200_index *ix, int device, int dim, int64_t n, double **dst, int64_t *ld) {
+    if (!ix) return LDA_B200_EINVAL;
+    if (device != ix->device) return ifail(ix, LDA_B200_EINVAL, "the index lives on device %d, the model on device %d", ix->device, device);
+    if (dim < 1 || n < 0) return ifail(ix, LDA_B200_EINVAL, "bad vector batch");
+    if (ix->dim && dim != ix->dim)
+        return ifail(ix, LDA_B200_EINVAL, "vector has %d elements, the index holds vectors of %d", dim, ix->dim);
+    if (ix->n + n >= (1LL << 32) - 1) return ifail(ix, LDA_B200_EUNSUPPORTED, "more than 2^32 - 2 vectors");
+    ICU(cudaSetDevice(ix->device));
+    ix->dim = dim;
+    ITRY(reserve(ix, n));
+    ICU(cudaStreamSynchronize(ix->stream));
+    *dst = ix->vec + ix->n;
+    *ld = ix->cap;
+    return 0;
+}
+
+int index_finish_append(lda_b200_index *ix, int64_t n, const int64_t *ids) {
+    if (!ix) return LDA_B200_EINVAL;
+    if (n <= 0) return 0;
+    ICU(cudaSetDevice(ix->device));
+    ICU(cudaMemcpyAsync(ix->ids + ix->n, ids, (size_t)n * sizeof(int64_t), cudaMemcpyHostToDevice, ix->stream));
+    index_norms_kernel<<<grid_for(n, 256, ix->sms * 8), 256, 0, ix->stream>>>(ix->vec, ix->cap, ix->dim, ix->n, n, ix->norm);
+    IKCHECK();
+    ICU(cudaStreamSynchronize(ix->stream));
+    ix->h_ids.insert(ix->h_ids.end(), ids, ids + n);
+    ix->n += n;
+    return 0;
+}
 
 extern "C" {
 

@@ -22,6 +22,8 @@
 #include <cub/device/device_scan.cuh>
 
 #include "../../include/lda_b200.h"
+#include "../../include/lda_b200_index.h"
+#include "index_internal.h"
 #include "kernels.cuh"
 #include "nccl_dl.h"
 #include "pcg.cuh"
@@ -1069,7 +1071,10 @@ inline double rho_calc(const lda_b200_schedule &s, double t) { return s.S / pow(
 // normalise/transpose (main stream), result out (down stream) -- so the host<->device transfers
 // of neighbouring ranges hide behind the kernel of the current one; otherwise it is one launch over all documents.  Documents are independent (lda.go:429-435), so the split changes
 // nothing but the longest-first order inside a launch.
-int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *theta_out, int32_t *passes_out_host) {
+// dev_out / dev_ld (optional): a device matrix that receives the K x Dl result (column l at dev_out + l, row pitch dev_ld)
+// instead of a host matrix -- the index's storage, see lda_b200_transform_into_index.
+int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *theta_out, int32_t *passes_out_host,
+                  double *dev_out = nullptr, int64_t dev_ld = 0) {
     const int T = h->cfg.transformation_passes;
     TRY(fill_rho_table(h, rho_theta_t, T + 1));
     const bool streamed = c.range_docs > 0;
@@ -1104,7 +1109,9 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *the
     };
     auto run = [&]() -> int {
         if (passes_out_host) TRY(dalloc(h, &dpass, (size_t)Dl));
-        if (theta_out && Dl > 0) TRY(dalloc(h, &dout, (size_t)h->K * Dl));
+        if (theta_out && !dev_out && Dl > 0) TRY(dalloc(h, &dout, (size_t)h->K * Dl));
+        double *sink = dev_out ? dev_out : dout;       // where normalise + transpose writes
+        const int64_t sink_ld = dev_out ? dev_ld : Dl;
         if (streamed) {  // the copy stream starts once everything queued so far has run
             CU(cudaEventRecord(h->copy_ev, h->stream));
             CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
@@ -1180,10 +1187,12 @@ int run_transform(lda_b200_handle *h, Corpus &c, double rho_theta_t, double *the
                 CU(cudaEventRecord(k1, cs));
                 ktime.push_back({k0, k1});
             }
-            if (dout) {
+            if (sink) {
                 transpose_out_kernel<true><<<(unsigned)((lb - la + 31) / 32), 256, 0, cs>>>(c.theta + la * h->Kp, lb - la, h->K, h->Kp,
-                                                                                                  nullptr, dout + la, Dl);
+                                                                                                  nullptr, sink + la, sink_ld);
                 KCHECK();
+            }
+            if (dout) {
                 Range cur{la, lb, nullptr};
                 TRY(new_event(&cur.done));
                 CU(cudaEventRecord(cur.done, cs));
@@ -2038,6 +2047,38 @@ int lda_b200_transform_matrix(lda_b200_handle *h, const lda_b200_matrix *m, cons
     MatrixView v;
     TRY(open_model_matrix(h, m, v));
     const int rc = transform_impl(h, v.D, v.indptr, v.ind, v.data, theta0, rnd, rho_theta_t, theta_out, passes_out, v.on_device);
+    free_device_csc(h, v.owned);
+    return rc;
+}
+
+// ColDo(lda.Transform(m), func(j, v) { index.Index(v, ids[j]) }) with the vectors staying in HBM: the Transform pipeline's
+// normalise + transpose kernel writes each range of documents straight into the index's [dim][cap] matrix.
+int lda_b200_transform_into_index(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
+                                  double rho_theta_t, lda_b200_index *ix, const int64_t *ids) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!ix) return fail(h, LDA_B200_EINVAL, "index is NULL");
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "Transform called before Fit / set_state");
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    MatrixView v;
+    TRY(open_model_matrix(h, m, v));
+    Corpus c;
+    auto run = [&]() -> int {
+        TRY(upload_corpus(h, c, h->W, v.D, v.indptr, v.ind, v.data, nullptr, false, false, v.on_device, kTransformRangeDocs));
+        TRY(init_theta(h, c, theta0, rnd, 0));
+        if (!theta0) advance(rnd, (uint64_t)v.D * (uint64_t)h->K);
+        double *dst = nullptr;
+        int64_t ld = 0;
+        if (index_begin_append(ix, h->device, h->K, c.Dl, &dst, &ld))
+            return fail(h, LDA_B200_EINVAL, "index: %s", lda_b200_index_last_error(ix));
+        TRY(run_transform(h, c, rho_theta_t, nullptr, nullptr, dst, ld));  // returns with every stream drained
+        std::vector<int64_t> new_ids((size_t)c.Dl);  // this rank's documents, in local order
+        for (const Segment &s : c.segs)
+            for (int64_t g = s.g0; g < s.g1; ++g) new_ids[(size_t)(s.l0 + g - s.g0)] = ids ? ids[g] : g;
+        if (index_finish_append(ix, c.Dl, new_ids.data())) return fail(h, LDA_B200_EINVAL, "index: %s", lda_b200_index_last_error(ix));
+        return 0;
+    };
+    const int rc = run();
+    free_corpus(h, c);
     free_device_csc(h, v.owned);
     return rc;
 }

@@ -25,8 +25,13 @@ class LinearScanIndex:
         if not isinstance(compareFN, pairwise.Comparer):
             raise TypeError("nlp: compareFN must be one of nlp_b200.measures.pairwise (the kernels are specialised on it)")
         self.distance = compareFN
-        self._ids = {}        # int64 handle -> caller's id (index.go:16: ID interface{})
+        # Vectors are known to the library by int64 handles (their insertion numbers).  Caller-chosen ids (index.go:16:
+        # ID interface{}) are kept in dictionaries; runs of default ids (consecutive integers) are kept as ranges, so that
+        # indexing a million columns costs no per-vector Python work.
+        self._ids = {}        # handle -> caller's id
         self._handles = {}    # caller's id -> handles in insertion order (Remove drops the first, index.go:121-122)
+        self._auto = []       # (first handle, end handle, first id) of runs with default ids, in insertion order
+        self._removed = set() # handles of removed default-id vectors
         self._next = 0
         self._dim = None      # fixed by the first vector
         h = C.c_void_p()
@@ -47,9 +52,9 @@ class LinearScanIndex:
     def __len__(self):
         return int(_lib.lib().lda_b200_index_len(self._h))
 
-    def _new_handles(self, ids):
-        out = np.arange(self._next, self._next + len(ids), dtype=np.int64)
-        self._next += len(ids)
+    def _new_handles(self, n):
+        out = np.arange(self._next, self._next + n, dtype=np.int64)
+        self._next += n
         return out
 
     def _register(self, handles, ids):
@@ -57,11 +62,34 @@ class LinearScanIndex:
             self._ids[hd] = id
             self._handles.setdefault(id, []).append(hd)
 
+    def _register_auto(self, handles, first_id):
+        if len(handles):
+            self._auto.append((int(handles[0]), int(handles[-1]) + 1, int(first_id)))
+
+    def _id_of(self, hd):
+        if hd in self._ids:
+            return self._ids[hd]
+        import bisect
+        i = bisect.bisect_right(self._auto, (hd, float("inf"), 0)) - 1
+        h0, _h1, id0 = self._auto[i]
+        return id0 + (hd - h0)
+
+    def _first_handle_of(self, id):
+        """the earliest-indexed live vector carrying this id, or None"""
+        best = self._handles[id][0] if self._handles.get(id) else None
+        if isinstance(id, (int, np.integer)) and not isinstance(id, bool):
+            for h0, h1, id0 in self._auto:
+                hd = h0 + (int(id) - id0)
+                if h0 <= hd < h1 and hd not in self._removed and (best is None or hd < best):
+                    best = hd
+                    break
+        return best
+
     # ---- reference API -----------------------------------------------------------------------------------
     def Index(self, v, id):
         """index.go:79-84"""
         v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel())
-        handles = self._new_handles([id])
+        handles = self._new_handles(1)
         _lib.check_index(_lib.lib().lda_b200_index_add(self._h, v.size, 1, _ptr(v), 1, _ptr(handles)), self._h)
         self._dim = v.size
         self._register(handles, [id])
@@ -73,13 +101,17 @@ class LinearScanIndex:
 
     def Remove(self, id):
         """index.go:117-135"""
-        hs = self._handles.get(id)
-        if not hs:
+        hd = self._first_handle_of(id)
+        if hd is None:
             return
-        hd = hs.pop(0)
-        if not hs:
-            del self._handles[id]
-        del self._ids[hd]
+        if hd in self._ids:
+            hs = self._handles[id]
+            hs.remove(hd)
+            if not hs:
+                del self._handles[id]
+            del self._ids[hd]
+        else:
+            self._removed.add(hd)
         _lib.check_index(_lib.lib().lda_b200_index_remove(self._h, hd), self._h)
 
     # ---- batched forms -------------------------------------------------------------------------------------
@@ -92,23 +124,46 @@ class LinearScanIndex:
         if not m.flags.c_contiguous:
             m = np.ascontiguousarray(m)
         n = m.shape[1]
-        if ids is None:
-            base = len(self)
-            ids = list(range(base, base + n))
-        if len(ids) != n:
+        if ids is not None and len(ids) != n:
             raise ValueError("nlp: one id per column")
-        handles = self._new_handles(ids)
+        first_id = len(self)
+        handles = self._new_handles(n)
         _lib.check_index(_lib.lib().lda_b200_index_add(self._h, m.shape[0], n, _ptr(m), max(n, 1), _ptr(handles)), self._h)
         if n:
             self._dim = m.shape[0]
-        self._register(handles, ids)
+        if ids is None:
+            self._register_auto(handles, first_id)
+        else:
+            self._register(handles, ids)
+
+    def IndexTransform(self, lda, m, ids=None, theta0=None):
+        """ColDo(lda.Transform(m), func(j, v) { index.Index(v, ids[j]) }) without the vectors leaving the GPU: the
+        Transform pipeline (lda.go:446-453) writes its K x D result straight into this index's storage.  ids default to
+        the column numbers of m."""
+        from .lda import as_matrix
+        desc, _rows, cols, _keep = as_matrix(m, lda.DeviceConvert)
+        h = lda._handle()
+        if theta0 is None and not lda.DeviceInit:
+            theta0 = lda._draws(cols, cols * lda.K)
+        theta0 = None if theta0 is None else np.ascontiguousarray(theta0, dtype=np.float64)
+        if ids is not None and len(ids) != cols:
+            raise ValueError("nlp: one id per column")
+        handles = self._new_handles(cols)
+        rc = _lib.lib().lda_b200_transform_into_index(h, desc, _ptr(theta0), lda.Rnd.src._s, lda.rhoThetaT, self._h, _ptr(handles))
+        _lib.check(rc, h)
+        if cols:
+            self._dim = lda.K
+        if ids is None:
+            self._register_auto(handles, 0)
+        else:
+            self._register(handles, list(ids))
 
     def SearchColumns(self, q, k):
         """Search for every column of the dim x nq matrix q in one pass over the index -> list of Match lists"""
         ids, dist, found = self.SearchRaw(q, k)
         out = []
         for i in range(ids.shape[0]):
-            out.append([Match(float(dist[i, r]), self._ids[int(ids[i, r])]) for r in range(int(found[i]))])
+            out.append([Match(float(dist[i, r]), self._id_of(int(ids[i, r]))) for r in range(int(found[i]))])
         return out
 
     def SearchRaw(self, q, k):

@@ -207,3 +207,46 @@ def test_committed_golden_vectors():
             assert [x.ID for x in got[i]] == want["ids"], case["comparer"]
             assert np.abs(np.array([x.Distance for x in got[i]]) - np.array(want["distances"])).max() <= DIST_ATOL
         index.Close()
+
+
+def test_transform_into_index_keeps_the_vectors_on_the_device():
+    """lda_b200_transform_into_index: ColDo(lda.Transform(m), index.Index) fused -- the Transform pipeline writes its
+    result straight into the index's storage.  Same vectors, hence bitwise the same search results, as the round trip
+    through the host; several pipeline ranges, custom ids, and more vectors appended afterwards."""
+    import corpus_synth
+    from nlp_b200 import rand
+    from nlp_b200.lda import CSC
+    W, D, K = 3000, 70_000, 16
+    fit = CSC(W, 400, *corpus_synth.generate(400, W, block=100, mean_distinct=30, n_topics=16))
+    held = CSC(W, D, *corpus_synth.generate(D, W, seed=77, block=8192, mean_distinct=8, n_topics=16))
+    lda = nlp_b200.NewLatentDirichletAllocation(K)
+    lda.Rnd = rand.New(rand.NewSource(0))
+    lda.Processes, lda.Iterations = 1, 5
+    lda.Fit(fit)
+    t0 = np.random.default_rng(3).random((D, K))
+    theta = lda.Transform(held, theta0=t0)
+    ids = [("doc", j) for j in range(D)]
+    via_host = nlp_b200.NewLinearScanIndex(pairwise.CosineDistance)
+    via_host.IndexColumns(theta, ids)
+    fused = nlp_b200.NewLinearScanIndex(pairwise.CosineDistance)
+    fused.IndexTransform(lda, held, ids=ids, theta0=t0)
+    assert len(fused) == len(via_host) == D
+    q = theta[:, [0, 1, 65_535, 65_536, D - 1, 12_345]]
+    a, b = via_host.SearchRaw(q, 7), fused.SearchRaw(q, 7)
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2])
+    assert [[m.ID for m in r] for r in via_host.SearchColumns(q, 7)] == [[m.ID for m in r] for r in fused.SearchColumns(q, 7)]
+    assert fused.Search(theta[:, 65_536], 1)[0].ID == ("doc", 65_536)
+    # the index keeps growing after a fused append, and a second fused append lands behind the first
+    fused.Index(theta[:, 5] * 3.0, "scaled copy of 5")
+    assert {m.ID for m in fused.Search(theta[:, 5], 2)} == {("doc", 5), "scaled copy of 5"}
+    fused.IndexTransform(lda, held, ids=[("again", j) for j in range(D)], theta0=t0)
+    assert len(fused) == 2 * D + 1
+    assert {m.ID for m in fused.Search(theta[:, 40_000], 2)} == {("doc", 40_000), ("again", 40_000)}
+    # a model / index dimension mismatch is an error, not a crash
+    other = nlp_b200.NewLinearScanIndex(pairwise.CosineDistance)
+    other.Index(np.ones(K + 1), 0)
+    with pytest.raises(_lib.LdaB200Error, match="elements"):
+        other.IndexTransform(lda, held, theta0=t0)
+    for x in (via_host, fused, other):
+        x.Close()
+    lda.Close()
