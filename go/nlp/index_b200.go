@@ -126,6 +126,40 @@ func (b *B200LinearScanIndex) IndexColumns(m *mat.Dense, ids []interface{}) {
 	}
 }
 
+// IndexTransform is ColDo(theta, func(j int, v mat.Vector) { index.Index(v, ids[j]) }) with theta, _ := lda.Transform(m),
+// fused: the doc-topic vectors go from the Transform kernels into the index without leaving the GPU.
+func (b *B200LinearScanIndex) IndexTransform(lda *LatentDirichletAllocation, m mat.Matrix, ids []interface{}) error {
+	b.lock.Lock()
+	defer b.lock.Unlock()
+	h, err := lda.handle()
+	if err != nil {
+		return err
+	}
+	desc, keep := matrix(m)
+	_, c := m.Dims()
+	handles := make([]C.int64_t, c)
+	for j := range handles {
+		handles[j] = C.int64_t(b.next + int64(j))
+	}
+	rnd := lda.pcg()
+	var hp *C.int64_t
+	if c > 0 {
+		hp = &handles[0]
+	}
+	rc := C.lda_b200_transform_into_index(h, &desc, nil, &rnd, C.double(lda.rhoThetaT), b.h, hp)
+	runtime.KeepAlive(keep)
+	if rc != 0 {
+		return lda.err()
+	}
+	lda.takePcg(rnd)
+	for j := 0; j < c; j++ {
+		b.ids[b.next] = ids[j]
+		b.rev[ids[j]] = append(b.rev[ids[j]], b.next)
+		b.next++
+	}
+	return nil
+}
+
 // Search is index.go:85-115; the matches come nearest first (the reference returns them in heap order).
 func (b *B200LinearScanIndex) Search(qv mat.Vector, k int) []Match {
 	b.lock.RLock()

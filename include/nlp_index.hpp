@@ -72,6 +72,17 @@ class LinearScanIndex {
     void IndexColumns(const mat::Dense &m, const std::vector<int64_t> *ids = nullptr) {
         check(lda_b200_index_add(h_, m.r, m.c, m.data.data(), m.c, ids ? ids->data() : nullptr));
     }
+    // ColDo(theta, func(j, v) { index.Index(v, ids[j]) }) with theta = lda.Transform(m), fused: the vectors go from the
+    // Transform kernels into the index without leaving the GPU (lda_b200_transform_into_index); ids default to 0..D-1
+    template <class M>
+    void IndexTransform(LatentDirichletAllocation &lda, const M &m, const std::vector<int64_t> *ids = nullptr) {
+        std::string e;
+        lda_b200_handle *lh = lda.DeviceHandle(e);
+        if (!lh) throw std::runtime_error(e);
+        const lda_b200_matrix d = LatentDirichletAllocation::describe(m);
+        if (lda_b200_transform_into_index(lh, &d, nullptr, &lda.Rnd.src.s, lda.RhoThetaT(), h_, ids ? ids->data() : nullptr))
+            throw std::runtime_error(std::string("nlp: ") + lda_b200_last_error(lh));
+    }
     // index.go:85-115; matches come nearest first (the reference returns them in heap order)
     std::vector<Match> Search(const mat::VecDense &qv, int k) {
         std::vector<int64_t> ids((size_t)(k > 0 ? k : 1));

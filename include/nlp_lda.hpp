@@ -154,6 +154,11 @@ class LatentDirichletAllocation {
         if (!e.empty()) throw std::runtime_error(e);
         return out;
     }
+    // for LinearScanIndex::IndexTransform (nlp_index.hpp): the device-side handle (created on first use) and the private
+    // counter that Transform hands to burnInDoc (lda.go:231)
+    lda_b200_handle *DeviceHandle(std::string &err) { return handle(err) ? h_ : nullptr; }
+    double RhoThetaT() const { return rhoThetaT_; }
+
     // lda.go:414-416: K x W
     mat::Dense Components() {
         std::string e;

@@ -106,12 +106,36 @@ static void TestColumnsAndComparers() {
     if (!std::isnan(nlp::pairwise::CosineDistance(a, z))) Errorf("CosineDistance of a zero vector should be NaN\n");
 }
 
+// not in the reference: LDA's Transform feeding the index on the device (lda_b200_transform_into_index)
+static void TestIndexTransform() {
+    const std::vector<double> dataA = {
+        3, 3, 3, 0, 0, 0, 0, 0, 0, 3, 3, 3, 0, 0, 0, 0, 0, 0, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 3, 3, 3, 0, 0, 0, 0, 0, 0, 3, 3,
+        3, 0, 0, 0, 0, 0, 0, 3, 3, 3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0, 0, 0, 0, 0, 0, 4, 4, 4, 0, 0, 0, 0, 0, 0, 4, 4, 4};
+    std::unique_ptr<nlp::LatentDirichletAllocation> lda(nlp::NewLatentDirichletAllocation(3));
+    lda->Rnd = nlp::rand::New(nlp::rand::NewSource(0));
+    nlp::mat::Dense in = nlp::mat::NewDense(9, 9, dataA);
+    nlp::mat::Dense theta;
+    std::string err;
+    if (!lda->FitTransform(in, theta, &err)) Errorf("%s\n", err.c_str());
+    std::unique_ptr<nlp::LinearScanIndex> index(nlp::NewLinearScanIndex(nlp::pairwise::CosineDistance));
+    index->IndexTransform(*lda, in);
+    if (index->Len() != 9) Errorf("Len expected 9 but is %lld\n", (long long)index->Len());
+    // documents 0-2, 3-5 and 6-8 use the same words (lda_test.go:26-36): a document's nearest neighbours are its own group
+    for (int j = 0; j < 9; ++j) {
+        std::vector<nlp::Match> matches = index->Search(nlp::mat::ColView(theta, j), 3);
+        if (matches.size() != 3) Errorf("Search expected 3 results but received %zu\n", matches.size());
+        for (const nlp::Match &mt : matches)
+            if (mt.ID / 3 != j / 3 || mt.Distance > 0.01) Errorf("document %d: neighbour %lld at distance %f\n", j, (long long)mt.ID, mt.Distance);
+    }
+}
+
 int main() {
     try {
         TestIndexerIndex();
         TestIndexerSearch();
         TestIndexerRemove();
         TestColumnsAndComparers();
+        TestIndexTransform();
     } catch (const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 100;
