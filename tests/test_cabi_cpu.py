@@ -213,6 +213,18 @@ def test_bench_reference_arm_prints_one_json_line():
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
 
 
+def test_bench_cuda_arm_refuses_to_run_without_a_gpu():
+    # no CPU fallback: the CUDA arm of bench.py must stop, not time something else
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--workload", "C1", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout) and not r.stdout.strip().startswith("{")
+
+
 def test_matrix_descriptors_keep_the_callers_storage():
     """as_matrix hands CSR / CSC / dense inputs to the library in the storage they already have (lda_b200_matrix); other
     sparse formats and DeviceConvert = False go through the host-side ToCSC restatement (as_csc)"""
