@@ -7,5 +7,5 @@ after the path (section 8f) -- `LinearScanIndex` with the `pairwise` comparers o
 from .lda import (CSC, CSR, LatentDirichletAllocation, LearningSchedule,  # noqa: F401
                   NewLatentDirichletAllocation)
 from . import rand  # noqa: F401
-from .index import LinearScanIndex, Match, NewLinearScanIndex  # noqa: F401
+from .index import LinearScanIndex, Match, NewLinearScanIndex, SearchSharded, merge_matches  # noqa: F401
 from .measures import pairwise  # noqa: F401

@@ -193,6 +193,30 @@ class LinearScanIndex:
         return a.value, b.value, n.value, p.value
 
 
+def merge_matches(per_shard, k):
+    """The k nearest of the union of several shards' Search results (each a list of Match, nearest first): what a
+    LinearScanIndex over all the vectors would have returned, up to the order among exactly equal distances.  NaN
+    distances rank last, as in the index itself."""
+    import math
+    pool = [m for matches in per_shard for m in matches]
+    pool.sort(key=lambda m: (math.isnan(m.Distance), m.Distance if not math.isnan(m.Distance) else 0.0))
+    return pool[:k]
+
+
+def SearchSharded(index, q, k):
+    """Search over a sharded index: with one process per GPU (torch.distributed) every rank holds the vectors of its own
+    documents -- e.g. after IndexTransform under a communicator -- searches them, and the ranks' top-k lists are gathered
+    and merged.  The only exchange is k matches per query and rank; the vectors never move.  q: dim x nq matrix (the
+    same on every rank); returns a list of Match lists, identical on every rank."""
+    import torch.distributed as dist
+    local = index.SearchColumns(q, k)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return local
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, [[tuple(m) for m in row] for row in local])
+    return [merge_matches([[Match(*t) for t in shard[i]] for shard in gathered], k) for i in range(len(local))]
+
+
 def NewLinearScanIndex(compareFN, device=0):
     """index.go:74-76"""
     return LinearScanIndex(compareFN, device=device)

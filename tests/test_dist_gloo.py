@@ -77,3 +77,48 @@ def test_two_rank_step_algebra(D, b):
     ret = mp.Manager().dict()
     mp.spawn(_worker, args=(world, _free_port(), D, b, 40, 6, steps, ret), nprocs=world, join=True)
     assert dict(ret) == {0: 1, 1: 1}
+
+
+def _search_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import nlp_b200
+        from nlp_b200 import Match
+
+        class Shard:  # stands in for a LinearScanIndex holding this rank's documents (no GPU in the CPU suite)
+            def SearchColumns(self, q, k):
+                rng = np.random.default_rng(100 + rank)
+                vecs, ids = rng.random((q.shape[0], 50)), [rank * 1000 + j for j in range(50)]
+                out = []
+                for i in range(q.shape[1]):
+                    d = np.sqrt(((vecs - q[:, [i]]) ** 2).sum(0))
+                    order = np.argsort(d, kind="stable")[:k]
+                    out.append([Match(float(d[j]), ids[j]) for j in order])
+                return out
+
+        q = np.random.default_rng(7).random((6, 3))
+        ret[rank] = nlp_b200.SearchSharded(Shard(), q, 5)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_search_merges_the_ranks_top_k():
+    """SearchSharded: every rank searches its own shard, the top-k lists are gathered (k matches per query and rank) and
+    merged -- the result equals a search over the union of the shards and is identical on every rank"""
+    import torch.multiprocessing as mp
+    world, port = 2, _free_port()
+    with mp.Manager() as mgr:
+        ret = mgr.dict()
+        mp.spawn(_search_worker, args=(world, port, ret), nprocs=world, join=True)
+        got = [ret[r] for r in range(world)]
+    assert got[0] == got[1]
+    q = np.random.default_rng(7).random((6, 3))
+    vecs = np.concatenate([np.random.default_rng(100 + r).random((6, 50)) for r in range(world)], axis=1)
+    ids = [r * 1000 + j for r in range(world) for j in range(50)]
+    for i in range(3):
+        d = np.sqrt(((vecs - q[:, [i]]) ** 2).sum(0))
+        want = [ids[j] for j in np.argsort(d, kind="stable")[:5]]
+        assert [m.ID for m in got[0][i]] == want
+        assert all(a.Distance <= b.Distance for a, b in zip(got[0][i], got[0][i][1:]))
