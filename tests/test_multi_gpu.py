@@ -114,3 +114,62 @@ def test_two_gpu_fit_matches_sync_group_oracle(case, peer):
     p_want = o.Perplexity((W, 3 * b + 7) + tuple(held))
     assert abs(r0["perp"] / p_want - 1) <= 1e-3 and r0["perp"] == r1["perp"]
     assert r0["rnd"] == r1["rnd"] == o.rnd_state
+
+
+def _index_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import corpus_synth
+        import nlp_b200
+        from nlp_b200 import rand
+        from nlp_b200.lda import CSC
+        from nlp_b200.measures import pairwise
+        W, K, b, D = 600, 12, 64, 3 * 64 + 7
+        fit = CSC(W, 700, *corpus_synth.generate(700, W, block=b, mean_distinct=40, n_topics=16))
+        held = CSC(W, D, *corpus_synth.generate(D, W, seed=99, block=b, mean_distinct=40, n_topics=16))
+        lda = nlp_b200.NewLatentDirichletAllocation(K)
+        lda.Rnd = rand.New(rand.NewSource(0))
+        lda.Processes, lda.BatchSize, lda.Iterations = world, b, 4
+        lda.Fit(fit)
+        t0 = np.random.default_rng(5).random((D, K))
+        mine = lda.Transform(held, theta0=t0)                      # this rank's columns, zeros elsewhere
+        full = torch.from_numpy(mine).cuda(rank)
+        dist.all_reduce(full)
+        full = full.cpu().numpy()
+        index = nlp_b200.NewLinearScanIndex(pairwise.CosineDistance, device=rank)
+        index.IndexTransform(lda, held, theta0=t0)                 # sharded: only this rank's documents
+        q = full[:, [0, 63, 64, 130, D - 1]]
+        ret[rank] = dict(n=len(index), full=full, sharded=[[tuple(m) for m in row] for row in nlp_b200.SearchSharded(index, q, 4)])
+        index.Close()
+        lda.Close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_index():
+    """IndexTransform under a communicator indexes each rank's own documents; SearchSharded merges the ranks' top-k: the
+    result equals a search over all documents on one GPU"""
+    import torch
+    import torch.multiprocessing as mp
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import nlp_b200
+    from nlp_b200.measures import pairwise
+    ret = mp.Manager().dict()
+    mp.spawn(_index_worker, args=(2, _free_port(), ret), nprocs=2, join=True)
+    r0, r1 = ret[0], ret[1]
+    D = 3 * 64 + 7
+    assert r0["n"] + r1["n"] == D and r0["n"] == 2 * 64 and r0["sharded"] == r1["sharded"]
+    whole = nlp_b200.NewLinearScanIndex(pairwise.CosineDistance)
+    whole.IndexColumns(r0["full"])
+    want = whole.SearchColumns(r0["full"][:, [0, 63, 64, 130, D - 1]], 4)
+    for got_row, want_row, doc in zip(r0["sharded"], want, [0, 63, 64, 130, D - 1]):
+        assert got_row[0][1] == doc and abs(got_row[0][0]) <= 1e-12
+        assert [m[1] for m in got_row] == [m.ID for m in want_row]
+        assert np.abs(np.array([m[0] for m in got_row]) - np.array([m.Distance for m in want_row])).max() <= 1e-12
+    whole.Close()
