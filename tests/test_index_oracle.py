@@ -111,3 +111,60 @@ def test_committed_golden_vectors_reproduce():
             got = sorted(index.Search(q[:, i], case["k"]))
             assert [x.ID for x in got] == want["ids"]
             assert np.allclose([x.Distance for x in got], want["distances"], rtol=0, atol=1e-15)
+
+
+def _go_linear_scan(dist, ids, k):
+    """index.go:85-115 with Go's container/heap written out in Python (heap.Init / Pop / Push via up / down and
+    resultHeap.Less = larger distance first): an independent restatement that the C oracle must agree with match for
+    match, in heap order, ties included"""
+    less = lambda h, i, j: h[i][0] > h[j][0]
+
+    def up(h, j):
+        while True:
+            i = int((j - 1) / 2)   # Go's integer division truncates toward zero
+            if i == j or not less(h, j, i):
+                break
+            h[i], h[j] = h[j], h[i]
+            j = i
+
+    def down(h, i, n):
+        while True:
+            j1 = 2 * i + 1
+            if j1 >= n or j1 < 0:
+                break
+            j = j1
+            if j1 + 1 < n and less(h, j1 + 1, j1):
+                j = j1 + 1
+            if not less(h, j, i):
+                break
+            h[i], h[j] = h[j], h[i]
+            i = j
+
+    h = [(dist[p], ids[p]) for p in range(min(k, len(dist)))]
+    if len(h) < k:
+        return h
+    for i in range(len(h) // 2 - 1, -1, -1):
+        down(h, i, len(h))
+    for p in range(k, len(dist)):
+        if dist[p] <= h[0][0]:
+            n = len(h) - 1
+            h[0], h[n] = h[n], h[0]
+            down(h, 0, n)
+            h[n] = (dist[p], ids[p])
+            up(h, n)
+    return h
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_c_oracle_agrees_with_a_python_restatement_of_the_heap(seed):
+    rng = np.random.default_rng(seed)
+    n, dim, k = int(rng.integers(1, 120)), 4, int(rng.integers(1, 40))
+    m = rng.integers(0, 3, (dim, n)).astype(float)   # few distinct values: many exactly equal distances
+    q = rng.integers(0, 3, dim).astype(float)
+    index = I.LinearScanIndex("ManhattenDistance")
+    for j in range(n):
+        index.Index(m[:, j], 10 * j)
+    dist = [I.compare("ManhattenDistance", q, m[:, j]) for j in range(n)]
+    want = _go_linear_scan(dist, [10 * j for j in range(n)], k)
+    got = index.Search(q, k)
+    assert [(x.Distance, x.ID) for x in got] == want
