@@ -1,7 +1,15 @@
-import sys, time, os
+"""Timing of ColDo(lda.Transform(m), index.Index): through the host (Transform, then IndexColumns) against the fused
+device-resident hand-over (LinearScanIndex.IndexTransform -> lda_b200_transform_into_index) on 524,288 held-out documents,
+K = 256.  Needs a B200."""
+import os
+import sys
+import time
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
-import corpus_synth, nlp_b200
+import torch
+
+import corpus_synth
+import nlp_b200
 from nlp_b200 import rand
 from nlp_b200.lda import CSC
 from nlp_b200.measures import pairwise
