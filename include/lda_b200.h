@@ -113,7 +113,9 @@ void lda_b200_default_config(int32_t k, lda_b200_config *out);
 /* NewLatentDirichletAllocation, lda.go:145: allocates the model on CUDA device `device`. */
 int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle **out);
 void lda_b200_destroy(lda_b200_handle *h);
-/* exported fields may be changed between calls in Go; K may not change after a fit. */
+/* exported fields may be changed between calls in Go.  Changing K on a fitted model drops the model (nPhi / nZ are laid
+ * out for the old K): Transform / Perplexity / Components / get_state then fail with LDA_B200_ESTATE until the next fit
+ * or set_state. */
 int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg);
 /* error text of the last failed call on h (h == NULL: last failed create on this thread) */
 const char *lda_b200_last_error(const lda_b200_handle *h);

@@ -1536,6 +1536,11 @@ int lda_b200_set_config(lda_b200_handle *h, const lda_b200_config *cfg) {
     if (h->fit_open && cfg->K != h->cfg.K) return fail(h, LDA_B200_EINVAL, "K cannot change during a fit");
     const bool eta_changed = cfg->eta != h->cfg.eta;
     h->cfg = *cfg;
+    if (h->fitted && cfg->K != h->K) {
+        // nPhi / nZ are laid out for the old K: every later call sizes its buffers by the new one.  The model is dropped,
+        // so Transform / Perplexity / Components / get_state fail with ESTATE until the next Fit or set_state.
+        h->fitted = false;
+    }
     if (eta_changed && h->fitted && !h->fit_open && h->K == cfg->K) {
         CU(cudaSetDevice(h->device));
         TRY(refresh_inv_z(h));  // invZ and c = (nPhi + eta) invZ depend on Eta
@@ -1605,6 +1610,7 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     CU(cudaSetDevice(h->device));
     PhaseTimer pt(h->stream);
     h->fit_open = false;
+    if (!warm) h->fitted = false;  // nPhi / nZ are re-drawn below: a fit that fails half-way leaves no model behind
     // init (lda.go:193-206): nPhi/nZ are re-initialised on every fit, no warm start.  The device buffers (and the
     // peer mappings) are kept when the shape is unchanged; every value in them is rewritten below.
     const bool same_shape = h->nphi && h->W == W && h->K == h->cfg.K && (h->nranks == 1 || h->peer_ok || !h->peer_wanted);
@@ -1890,7 +1896,10 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             int bad = 0;
             CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
-            if (bad == 1) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)h->W);
+            if (bad == 1) {
+                h->fitted = false;  // the first iteration already blended statistics of the clamped ids into nPhi / nZ
+                return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)h->W);
+            }
         }
         h->it_done++;
         ran++;
@@ -2121,7 +2130,7 @@ int lda_b200_components(lda_b200_handle *h, double *out) {
 int lda_b200_get_dims(const lda_b200_handle *h, int64_t *W, int32_t *K) {
     if (!h) return LDA_B200_EINVAL;
     if (W) *W = h->W;
-    if (K) *K = h->cfg.K;
+    if (K) *K = h->fitted ? h->K : h->cfg.K;
     return 0;
 }
 

@@ -534,6 +534,36 @@ def test_errors():
     assert np.abs(t.sum(0) - 1).max() <= 1e-8  # still usable
 
 
+def test_changing_k_after_fit_drops_the_model():
+    """lda.K is an exported field (lda.go:92).  nPhi / nZ on the device are laid out for the K of the fit, and callers
+    size their result buffers by the new one, so a changed K must not reach Transform / Components / GetState."""
+    lda = new_lda(3, Iterations=3)
+    lda.Fit(FIXTURE_A)
+    assert lda.Components().shape == (3, 9)
+    lda.K = 2
+    for call in (lambda: lda.Transform(FIXTURE_A), lambda: lda.Perplexity(FIXTURE_A), lda.Components, lda.GetState):
+        with pytest.raises(_lib.LdaB200Error, match="before Fit|no model state"):
+            call()
+    lda.Fit(FIXTURE_A)      # a new fit with the new K works
+    assert lda.Transform(FIXTURE_A).shape == (2, 9) and lda.Components().shape == (2, 9)
+    lda.K = 5               # and so does loading a state of the new shape
+    lda.SetState(np.random.default_rng(0).random((9, 5)), np.ones(5))
+    assert lda.Transform(FIXTURE_A).shape == (5, 9)
+
+
+def test_failed_fit_leaves_no_model():
+    """out-of-range word ids are found while the first iteration already runs (they stream in behind the first
+    launches); the fit fails and must not leave a half-trained model behind that Transform would accept"""
+    lda = new_lda(3, Iterations=2)
+    lda.Fit(FIXTURE_A)
+    bad = as_csc(FIXTURE_A)
+    bad.ind[4] = 9
+    with pytest.raises(_lib.LdaB200Error, match="outside"):
+        lda.Fit(bad)
+    with pytest.raises(_lib.LdaB200Error, match="before Fit"):
+        lda.Transform(FIXTURE_A)
+
+
 # ---- size-independent properties at a BASELINE-sized configuration -----------------------------------------------------
 def test_config2_properties():
     """configs[1] shape (18,846 docs x 50k vocab, K=100): columns sum to 1, perplexity ends up falling, refit reproducible

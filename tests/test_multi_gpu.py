@@ -1,6 +1,8 @@
-"""N = 2 ranks, one process per GPU, NCCL: the sharded fit must match the oracle's SyncGroup = 2 restatement
-(minibatches 2s, 2s+1 computed from the same nPhi snapshot, blended in index order -- SURVEY.md 8e), and the sharded
-Transform must match the single-GPU result.  Needs >= 2 GPUs (gpurun --gpus 2)."""
+"""R ranks (one process per GPU, NCCL) x C minibatches per GPU and step: the sharded fit must match the oracle's
+SyncGroup = R*C restatement (minibatches sG .. sG+G-1 computed from the same nPhi snapshot, blended in index order --
+SURVEY.md 8e, lda.go:487-528), and the sharded Transform / Perplexity must match the oracle under the same model.
+R = 2 needs `gpurun --gpus 2`; the R = 4 and R = 8 cases run when the box has that many GPUs and are skipped otherwise.
+R x C = 4 per GPU is the configuration bench.py's scaling runs use (Processes = 4 per GPU)."""
 import os
 import socket
 import sys
@@ -20,7 +22,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, case, peer, ret):
+def _owned_view(indptr, ind, data, D, b, rank, world):
+    """this rank's view of the corpus: other ranks' documents are empty (the library must not need them)"""
+    keep = np.zeros(D, dtype=bool)
+    for m in range(rank, (D + b - 1) // b, world):
+        keep[m * b:(m + 1) * b] = True
+    lens = np.diff(indptr) * keep
+    sel = np.repeat(keep, np.diff(indptr))
+    return np.concatenate(([0], np.cumsum(lens))), ind[sel], data[sel]
+
+
+def _worker(rank, world, port, case, conc, peer, ret):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank),
                       LDA_B200_PEER_MEMORY="1" if peer else "0")
@@ -35,18 +47,12 @@ def _worker(rank, world, port, case, peer, ret):
         from nlp_b200.lda import CSC
         D, W, K, b, iters = case
         indptr, ind, data = corpus_synth.generate(D, W, block=b, mean_distinct=40, n_topics=16)
-        if rank == 1:
-            # this rank's view: other ranks' documents are empty (the library must not need them)
-            keep = np.zeros(D, dtype=bool)
-            for m in range(rank, (D + b - 1) // b, world):
-                keep[m * b:(m + 1) * b] = True
-            lens = np.diff(indptr) * keep
-            sel = np.repeat(keep, np.diff(indptr))
-            indptr, ind, data = np.concatenate(([0], np.cumsum(lens))), ind[sel], data[sel]
+        if rank >= 1:
+            indptr, ind, data = _owned_view(indptr, ind, data, D, b, rank, world)
         m = CSC(W, D, indptr, ind, data)
         lda = nlp_b200.NewLatentDirichletAllocation(K)
         assert lda.Device == rank and lda.Processes >= world
-        lda.Processes = world   # one minibatch per GPU and step: the oracle's SyncGroup = world
+        lda.Processes = world * conc   # conc minibatches per GPU and step: the oracle's SyncGroup = world * conc
         lda.Rnd = rand.New(rand.NewSource(0))
         lda.BatchSize, lda.Iterations = b, iters
         lda.PerplexityEvaluationFrequency, lda.PerplexityTolerance = 1, 0.0
@@ -63,48 +69,72 @@ def _worker(rank, world, port, case, peer, ret):
         dist.destroy_process_group()
 
 
+# (ranks R, minibatches per GPU and step C, (D, W, K, BatchSize, iterations)); G = R*C minibatches share an nPhi snapshot.
+# D is chosen so that the last step is short (fewer than G minibatches) and the last minibatch is short (lda.go:268).
+CASES = [
+    (2, 1, (700, 600, 12, 64, 5)),
+    (2, 1, (1030, 800, 256, 128, 3)),
+    (2, 4, (2 * 8 * 64 + 3 * 64 + 17, 600, 12, 64, 4)),       # bench.py's Processes = 4 per GPU, narrow-K kernels
+    (2, 4, (2 * 8 * 96 + 5 * 96 + 9, 900, 256, 96, 3)),       # ... and the K = 256 throughput kernel
+    (4, 1, (4 * 3 * 64 + 2 * 64 + 5, 600, 12, 64, 4)),
+    (4, 4, (2 * 16 * 64 + 7 * 64 + 11, 900, 256, 64, 3)),
+    (8, 1, (8 * 3 * 48 + 5 * 48 + 5, 600, 12, 48, 4)),
+    (8, 4, (2 * 32 * 48 + 13 * 48 + 7, 900, 256, 48, 3)),      # the N = 8 configuration of the scaling runs (G = 32)
+]
+
+
+def _ids(c):
+    return "R%dxC%d-K%d-D%d" % (c[0], c[1], c[2][2], c[2][0])
+
+
 @pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl-allreduce"])
-@pytest.mark.parametrize("case", [(700, 600, 12, 64, 5), (1030, 800, 256, 128, 3)])
-def test_two_gpu_fit_matches_sync_group_oracle(case, peer):
+@pytest.mark.parametrize("cfg", CASES, ids=_ids)
+def test_multi_gpu_fit_matches_sync_group_oracle(cfg, peer):
     """peer=True: reduction + M-step fused in one kernel over NVLink peer memory (CUDA IPC); peer=False: the
-    ncclAllReduce + blend fallback.  Both must give the same model."""
+    ncclAllReduce + blend fallback.  Both must give the same model as the oracle's SyncGroup = R*C schedule."""
     import torch
     import torch.multiprocessing as mp
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    R, conc, case = cfg
+    if torch.cuda.device_count() < R:
+        pytest.skip("needs %d GPUs" % R)
     import corpus_synth
     from oracle import oracle as O
     D, W, K, b, iters = case
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(2, _free_port(), case, peer, ret), nprocs=2, join=True)
-    r0, r1 = ret[0], ret[1]
+    mp.spawn(_worker, args=(R, _free_port(), case, conc, peer, ret), nprocs=R, join=True)
+    rs = [ret[r] for r in range(R)]
+    r0 = rs[0]
 
     indptr, ind, data = corpus_synth.generate(D, W, block=b, mean_distinct=40, n_topics=16)
     o = O.LatentDirichletAllocation(K, seed=0)
-    o.BatchSize, o.Iterations, o.SyncGroup = b, iters, 2
+    o.BatchSize, o.Iterations, o.SyncGroup = b, iters, R * conc
     o.PerplexityEvaluationFrequency, o.PerplexityTolerance = 1, 0.0
     want = o.FitTransform((W, D, indptr, ind, data))
 
     # every rank wrote only its own documents' columns
-    own0 = np.zeros(D, dtype=bool)
-    for m in range(0, (D + b - 1) // b, 2):
-        own0[m * b:(m + 1) * b] = True
-    assert np.all(r0["theta"][:, ~own0] == 0) and np.all(r1["theta"][:, own0] == 0)
-    theta = r0["theta"] + r1["theta"]
+    theta = np.zeros_like(want)
+    for r in range(R):
+        own = np.zeros(D, dtype=bool)
+        for m in range(r, (D + b - 1) // b, R):
+            own[m * b:(m + 1) * b] = True
+        assert np.all(rs[r]["theta"][:, ~own] == 0)
+        theta += rs[r]["theta"]
     assert np.abs(theta - want).max() <= 2e-3
     np.testing.assert_allclose(r0["trace"], o.perplexity_trace, rtol=1e-3)
-    assert r0["trace"] == r1["trace"]                       # allreduced partial sums: identical on both ranks
-    assert np.array_equal(r0["nphi"], r1["nphi"]) and np.array_equal(r0["nz"], r1["nz"])  # bitwise-identical replicas
     nphi_o, nz_o = o.get_state()
     np.testing.assert_allclose(r0["nz"], nz_o, rtol=1e-3)
-    assert r0["counters"] == r1["counters"] == (o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus)
+    for r in rs[1:]:
+        assert r["trace"] == r0["trace"]                       # allreduced partial sums: identical on every rank
+        assert np.array_equal(r0["nphi"], r["nphi"]) and np.array_equal(r0["nz"], r["nz"])  # bitwise-identical replicas
+        assert r["counters"] == r0["counters"] and r["rnd"] == r0["rnd"]
+    assert r0["counters"] == (o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus)
 
     # sharded Transform / Perplexity (no collective on the data path) against the oracle under the same model
     o.set_state(r0["nphi"], r0["nz"])
     held = corpus_synth.generate(3 * b + 7, W, seed=99, block=b, mean_distinct=40, n_topics=16)
     t_want, p_want_passes = o.Transform((W, 3 * b + 7) + tuple(held), return_passes=True)
-    t = r0["transform"] + r1["transform"]
-    passes = r0["passes"] + r1["passes"]      # each rank fills only its own documents
+    t = sum(r["transform"] for r in rs)
+    passes = sum(r["passes"] for r in rs)      # each rank fills only its own documents
     same = passes == p_want_passes
     # burnInDoc can only stop at multiples of 30 passes (lda.go:224-259); a borderline fp32/float64 decision shifts a
     # document by 30 passes, which the reference's own test tolerates with 0.035 (lda_test.go:231)
@@ -112,8 +142,8 @@ def test_two_gpu_fit_matches_sync_group_oracle(case, peer):
     assert np.abs(t - t_want)[:, same].max() <= 2e-3
     assert np.abs(t - t_want).max() <= 0.035
     p_want = o.Perplexity((W, 3 * b + 7) + tuple(held))
-    assert abs(r0["perp"] / p_want - 1) <= 1e-3 and r0["perp"] == r1["perp"]
-    assert r0["rnd"] == r1["rnd"] == o.rnd_state
+    assert abs(r0["perp"] / p_want - 1) <= 1e-3 and all(r["perp"] == r0["perp"] for r in rs)
+    assert r0["rnd"] == o.rnd_state
 
 
 def _index_worker(rank, world, port, ret):
