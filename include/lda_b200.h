@@ -59,7 +59,7 @@ typedef struct {
     int32_t perplexity_evaluation_frequency;/* lda.go:79  */
     int32_t change_evaluation_frequency;    /* lda.go:103 */
     int32_t processes;                      /* lda.go:134 Processes: minibatches in flight per step.  With R ranks
-                                               each GPU processes max(1, processes / R) (at most 16) consecutive
+                                               each GPU processes max(1, processes / R) (at most 256) consecutive
                                                minibatches of its own in one launch, all from the same nPhi
                                                snapshot, blended afterwards in index order (lda.go:299-317) */
     double perplexity_tolerance;            /* lda.go:75  */
@@ -250,6 +250,13 @@ int64_t lda_b200_launch_count(const lda_b200_handle *h);
  * lda_b200_fit_iterate call, and the number of its launches (roofline leg of bench.py) */
 int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
                               float *blend_ms, int32_t *blend_launches);
+
+/* Diagnostic for the roofline leg of bench.py: what the memory system delivers for the access mix of the minibatch
+ * kernel with the arithmetic and the per-document dependency chain taken away.  Replays the word ids of the first launch
+ * range of the resident corpus (between lda_b200_fit_begin and lda_b200_fit_end): (BurnInPasses+1) coalesced reads of the
+ * 4*K-byte row of C per entry (gather_ms), one red.global.add.v4.f32 of a row into nPhiHat per entry (red_ms; adds zeros,
+ * the model is unchanged), and both together (mix_ms).  entries = entries replayed.  Best of three launches each. */
+int lda_b200_probe_memory_mix(lda_b200_handle *h, int64_t *entries, float *gather_ms, float *red_ms, float *mix_ms);
 
 /* which multi-GPU step path the last fit used: peer_memory_path = 1 when the reduction of nPhiHat and the M-step run
  * as one kernel over NVLink peer memory (CUDA IPC), 0 when ncclAllReduce + blend is used (fallback, or

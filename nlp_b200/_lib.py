@@ -84,6 +84,8 @@ SYMBOLS = {
                                             C.POINTER(C.c_int32)]),
     "lda_b200_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lda_b200_last_allreduce_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "lda_b200_probe_memory_mix": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float)]),
 }
 
 # every symbol include/lda_b200_index.h declares

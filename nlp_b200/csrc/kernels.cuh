@@ -71,14 +71,16 @@ struct DocsArgs {
     // sufficient-statistics scale of each minibatch covered by this launch: wordsInCorpus / batchSize (lda.go:293)
     // times the coefficient of that minibatch in the combined blend (lda_b200_plan_step); a launch covers up to
     // MAX_CONCURRENT_MB consecutive local minibatches of mb_docs documents (the reference's `Processes`).
-    float hat_scale[16];
+    float hat_scale[256];
     int mb_docs;
+    int mb_origin;           // first document of the step's launch range: minibatch slot = (doc - mb_origin) / mb_docs
+                             // (a step may be issued as several launches over sub-ranges of its documents)
     // deterministic mode: the sufficient statistics are accumulated as 64-bit fixed-point integers (value * fx_scale,
     // fx_scale a power of two), whose atomic sums do not depend on the order in which the warps arrive
     unsigned long long *hat_fx;  // [W][Kp]
     float fx_scale;
 };
-constexpr int MAX_CONCURRENT_MB = 16;
+constexpr int MAX_CONCURRENT_MB = 256;
 
 // One pass over the tokens of the documents currently held by this warp's groups.
 //   Eqn 5 (lda.go:234-242 / 277-284): gamma_k ∝ (nPhi[i,k]+eta)(nTheta[j,k]+alpha)/(nZ[k]+eta*W), normalised
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(256) scvb0_docs_kernel(const DocsArgs a) {
         }
         if (FIT) {
             const float l1m = a.log1m_rho[a.passes];  // lda.go:274
-            const float hs = valid ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
+            const float hs = valid ? a.hat_scale[(doc - a.mb_origin) / a.mb_docs] : 0.f;
             token_pass<LANES, NV, P, true, DET>(a, base, len, maxlen, l1m, wcj, hs, g, th, ok);
         }
         if (valid) {
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
             continue;
         }
         const float wcj = a.wc[doc];
-        const float hat_scale = FIT ? a.hat_scale[(doc - a.doc_begin) / a.mb_docs] : 0.f;
+        const float hat_scale = FIT ? a.hat_scale[(doc - a.mb_origin) / a.mb_docs] : 0.f;
         float *trow = a.theta + (int64_t)doc * Kp + 4 * lane;
         float4 tha[NV];
 #pragma unroll
@@ -1101,6 +1103,50 @@ __global__ void __launch_bounds__(256) doc_wc_kernel(const int64_t *doc_ptr, con
         for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
         partials[blockIdx.x] = s;
     }
+}
+
+// ---- diagnostic: the memory access mix of the minibatch kernel without its arithmetic ---------------------------------
+// What the memory system delivers for the token stream of one launch when nothing depends on anything: `gathers` reads of
+// the 4*Kp-byte row of C per token (ld.global.cg, U rows in flight per warp) and, with RED, one red.global.add.v4.f32 of
+// a row of zeros into nPhiHat (adding +0 leaves the statistics unchanged; the L2 atomic units do the same work).  The
+// time of this kernel is the floor the minibatch kernel's duration is compared with (bench.py).
+template <bool RED, int U>
+__global__ void __launch_bounds__(256) memory_mix_probe_kernel(const float *cmat, float *hat, const int32_t *ind, int64_t n, int Kp,
+                                                               int gathers, float *sink) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int vecs = Kp >> 2;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t t0 = warp * U; t0 < n; t0 += nwarps * U) {
+        int w[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) w[u] = t0 + u < n ? ind[t0 + u] : -1;
+        for (int g = 0; g < gathers; ++g) {
+            for (int v = lane; v < vecs; v += 32) {
+                float4 r[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (w[u] >= 0) r[u] = __ldcg(reinterpret_cast<const float4 *>(cmat + (int64_t)w[u] * Kp) + v);
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (w[u] >= 0) {
+                        acc.x += r[u].x;
+                        acc.y += r[u].y;
+                        acc.z += r[u].z;
+                        acc.w += r[u].w;
+                    }
+            }
+            // the next pass over the document fetches the same rows again (they do not stay on chip in between)
+        }
+        if (RED) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (w[u] >= 0)
+                    for (int v = lane; v < vecs; v += 32) red_add_v4(hat + (int64_t)w[u] * Kp + 4 * v, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
+    }
+    if (acc.x + acc.y + acc.z + acc.w == 123.456f) *sink = acc.x;  // keeps the loads alive
 }
 
 }  // namespace ldab

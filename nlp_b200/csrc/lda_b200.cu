@@ -46,6 +46,11 @@ struct Corpus {
     int64_t nnz = 0;     // local non-zeros
     int64_t b = 0;       // block (minibatch) size used for sharding
     int conc = 1;        // minibatches per launch on this GPU (Processes / ranks), fit only
+    int64_t sub = 0;     // fit: documents per sub-range of a step's launch range (a multiple of b).  The longest-first order is
+                         // per sub-range, so a step can run as one launch over its whole range or as one launch per
+                         // sub-range -- the latter while word ids still stream in (first iteration) or results stream
+                         // out (last iteration), so that the transfers overlap the neighbouring launches
+    std::vector<int64_t> sub_begin;  // first local document of every sub-range, ascending
     std::vector<Segment> segs;
     int64_t *doc_ptr = nullptr;
     int32_t *ind = nullptr;
@@ -56,7 +61,7 @@ struct Corpus {
                            // documents only interact through commutative sums)
     // word ids may still be arriving on the copy stream during the first iteration of lda_b200_fit: one event per launch
     // range, recorded when that range's ids are in place
-    std::vector<cudaEvent_t> range_ev;
+    std::vector<cudaEvent_t> range_ev;  // one per sub-range (sub_begin)
     bool ind_deferred = false;
     double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
     // where the entries come from (the caller's arrays, valid for the duration of the call) and the local indptr: data
@@ -836,6 +841,14 @@ int upload_part(lda_b200_handle *h, Corpus &c, int64_t la, int64_t lb, cudaStrea
     return 0;
 }
 
+// a step's launch range of more documents than this is tiled into sub-ranges (see Corpus::sub); LDA_B200_SUB_RANGE_DOCS
+// overrides it (tests exercise the sub-range path on small corpora)
+int64_t fit_sub_range_docs() {
+    const char *env = getenv("LDA_B200_SUB_RANGE_DOCS");
+    const long long v = env ? atoll(env) : 0;
+    return v > 0 ? (int64_t)v : 32768;
+}
+
 // Uploads this rank's shard of the CSC (token order preserved, ids narrowed exactly) and computes wc / N.
 // src_device: ind / data are device arrays (a matrix converted on the device, see DeviceCSC); indptr is always on the host.
 // range_docs > 0 (Transform / Perplexity): only the plan is made here -- local indptr, launch order per range of
@@ -896,9 +909,16 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         // copies above are in flight.
         std::vector<int> ord((size_t)Dl);
         std::vector<int> cnt;
-        const int64_t blk = per_minibatch_order ? c.b * c.conc : streamed ? range_docs : std::max<int64_t>(Dl, 1);
-        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
-            const int64_t l1 = std::min(Dl, l0 + blk);
+        const int64_t range = per_minibatch_order ? c.b * c.conc : streamed ? range_docs : std::max<int64_t>(Dl, 1);
+        c.sub = range;
+        const int64_t sub_docs = fit_sub_range_docs();
+        if (per_minibatch_order && range > sub_docs) c.sub = std::max<int64_t>(1, sub_docs / c.b) * c.b;
+        c.sub_begin.clear();
+        for (int64_t r0 = 0; r0 < Dl; r0 += range)
+            for (int64_t l0 = r0; l0 < std::min(Dl, r0 + range); l0 += c.sub) c.sub_begin.push_back(l0);
+        for (size_t si = 0; si < c.sub_begin.size(); ++si) {
+            const int64_t l0 = c.sub_begin[si];
+            const int64_t l1 = std::min({Dl, l0 + c.sub, (l0 / range + 1) * range});
             int64_t maxlen = 0;
             for (int64_t l = l0; l < l1; ++l) maxlen = std::max(maxlen, lp[l + 1] - lp[l]);
             cnt.assign((size_t)maxlen + 2, 0);
@@ -923,13 +943,14 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
     memcpy(&bad, h->h_pinned + 1, sizeof(int));
     if (bad) return fail(h, LDA_B200_EINVAL, "a row index lies outside [0, %lld)", (long long)W);
     if (defer_ind) {
-        // The stage buffer now belongs to the copy stream: the ids of launch range r (conc minibatches) are sent, narrowed
-        // and signalled with range_ev[r]; the first iteration's launches wait on their own range only.
-        const int64_t blk = c.b * c.conc;
+        // The stage buffer now belongs to the copy stream: the ids of sub-range i are sent, narrowed and signalled with
+        // range_ev[i]; the first iteration's launches wait on their own sub-range only.
+        const int64_t range = c.b * c.conc;
         CU(cudaEventRecord(h->copy_ev, h->stream));
         CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
-        for (int64_t l0 = 0; l0 < Dl; l0 += blk) {
-            TRY(upload_part(h, c, l0, std::min(Dl, l0 + blk), h->copy_stream, false, true));
+        for (size_t si = 0; si < c.sub_begin.size(); ++si) {
+            const int64_t l0 = c.sub_begin[si];
+            TRY(upload_part(h, c, l0, std::min({Dl, l0 + c.sub, (l0 / range + 1) * range}), h->copy_stream, false, true));
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c.range_ev.push_back(e);
@@ -1058,6 +1079,7 @@ DocsArgs docs_args(lda_b200_handle *h, const Corpus &c, int passes) {
     a.eta = (float)h->cfg.eta;
     for (float &x : a.hat_scale) x = 0.f;
     a.mb_docs = (int)std::max<int64_t>(1, c.b);
+    a.mb_origin = 0;
     a.hat_fx = nullptr;
     a.fx_scale = 1.f;
     return a;
@@ -1610,7 +1632,15 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     CU(cudaSetDevice(h->device));
     PhaseTimer pt(h->stream);
     h->fit_open = false;
-    if (!warm) h->fitted = false;  // nPhi / nZ are re-drawn below: a fit that fails half-way leaves no model behind
+    // what can be checked without touching the model is checked first: a call that fails here leaves the previous
+    // model as it was
+    if (D < 0) return fail(h, LDA_B200_EINVAL, "negative document count");
+    if (!indptr) return fail(h, LDA_B200_EINVAL, "indptr is NULL");
+    for (const Segment &sg : make_segments(D, h->cfg.batch_size, h->rank, h->nranks))
+        for (int64_t g = sg.g0; g < sg.g1; ++g)
+            if (indptr[g + 1] < indptr[g] || indptr[g] < 0)
+                return fail(h, LDA_B200_EINVAL, "indptr is not non-decreasing at column %lld", (long long)g);
+    if (!warm) h->fitted = false;  // nPhi / nZ are re-drawn below: a fit that fails from here on leaves no model behind
     // init (lda.go:193-206): nPhi/nZ are re-initialised on every fit, no warm start.  The device buffers (and the
     // peer mappings) are kept when the shape is unchanged; every value in them is rewritten below.
     const bool same_shape = h->nphi && h->W == W && h->K == h->cfg.K && (h->nranks == 1 || h->peer_ok || !h->peer_wanted);
@@ -1771,9 +1801,8 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             }
             if (l_first >= 0) {
                 Nvtx mb_range("lda_b200: minibatch launch (burn-in + sufficient statistics)");
-                a.doc_begin = (int)(l_first * b);
-                a.doc_end = (int)std::min<int64_t>(c.Dl, (l_last + 1) * b);
-                if (c.ind_deferred) CU(cudaStreamWaitEvent(h->stream, c.range_ev[(size_t)(l_first / c.conc)], 0));
+                const int64_t r0 = l_first * b, r1 = std::min<int64_t>(c.Dl, (l_last + 1) * b);
+                a.mb_origin = (int)r0;
                 int slot;
                 TRY(ev_begin(h, 0, &slot));
                 double inv_fx = 1.0;
@@ -1782,20 +1811,36 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                     // sums stay below hat_scale_max * documents; 2^e is the largest power of two that keeps them < 2^62
                     float smax = 0.f;
                     for (float x : a.hat_scale) smax = std::max(smax, fabsf(x));
-                    const double bound = std::max(1.0, (double)smax * (double)(a.doc_end - a.doc_begin));
+                    const double bound = std::max(1.0, (double)smax * (double)(r1 - r0));
                     const int e = std::max(-100, std::min(100, 61 - (int)ceil(log2(bound))));
                     a.hat_fx = h->hat_fx;
                     a.fx_scale = (float)ldexp(1.0, e);
                     inv_fx = ldexp(1.0, -e);
                 }
-                TRY(launch_docs<true>(h, a, c.order));
+                // one launch over the whole range, or one per sub-range while ids stream in / results stream out
+                const bool split = (stream_out || c.ind_deferred) && c.sub < r1 - r0;
+                const int64_t piece = split ? c.sub : r1 - r0;
+                for (int64_t s0 = r0; s0 < r1; s0 += piece) {
+                    const int64_t s1 = std::min(r1, s0 + piece);
+                    if (c.ind_deferred) {
+                        const size_t i0 = (size_t)(std::lower_bound(c.sub_begin.begin(), c.sub_begin.end(), s0) - c.sub_begin.begin());
+                        for (size_t i = i0; i < c.sub_begin.size() && c.sub_begin[i] < s1; ++i)
+                            CU(cudaStreamWaitEvent(h->stream, c.range_ev[i], 0));
+                    }
+                    if (s0 > r0) CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
+                    a.doc_begin = (int)s0;
+                    a.doc_end = (int)s1;
+                    TRY(launch_docs<true>(h, a, c.order));
+                    if (stream_out) TRY(stream_theta_range(h, c, s0, s1));
+                }
+                a.doc_begin = (int)r0;
+                a.doc_end = (int)r1;
                 if (h->hat_fx) {
                     const int64_t n = h->W * h->Kp;
                     hat_fx_to_float_kernel<<<grid_for(n, 256, h->sms * 8), 256, 0, h->stream>>>(h->hat_fx, h->nphi_hat, n, inv_fx);
                     KCHECK();
                 }
                 TRY(ev_end(h, slot));
-                if (stream_out) TRY(stream_theta_range(h, c, a.doc_begin, a.doc_end));
             }
             const double Ad = A, Cd = (n_s > 1) ? 1.0 : c_single;
             Nvtx m_range(h->peer_ok ? "lda_b200: exchange + M-step (peer memory)" : "lda_b200: exchange + M-step");
@@ -2297,6 +2342,55 @@ int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int
     if (blend_ms) *blend_ms = h->blend_ms;
     if (blend_launches) *blend_launches = h->blend_n;
     return 0;
+}
+
+// Memory floor of the minibatch kernel (diagnostic): replays the word ids of the first launch range of the resident
+// corpus through memory_mix_probe_kernel -- row gathers only, reductions only, and the kernel's own mix of BurnInPasses+1
+// gathers and one reduction per entry -- and reports the best of three timings of each.
+int lda_b200_probe_memory_mix(lda_b200_handle *h, int64_t *entries, float *gather_ms, float *red_ms, float *mix_ms) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!h->fit_open) return fail(h, LDA_B200_ESTATE, "lda_b200_probe_memory_mix needs a resident corpus (lda_b200_fit_begin)");
+    CU(cudaSetDevice(h->device));
+    const Corpus &c = h->fitc;
+    if (c.ind_deferred) CU(cudaStreamSynchronize(h->copy_stream));
+    const int64_t l1 = std::min<int64_t>(c.Dl, c.b * c.conc);
+    const int64_t n = c.lp.empty() ? 0 : c.lp[(size_t)l1];
+    if (entries) *entries = n;
+    if (n == 0) return fail(h, LDA_B200_EINVAL, "the first launch range holds no entries");
+    const int B = h->cfg.burn_in_passes;
+    float *sink = nullptr;
+    TRY(dalloc(h, &sink, 1));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int grid = h->sms * 8;
+    auto best_of = [&](int mode, float *out) -> int {
+        float best = 0.f;
+        for (int rep = 0; rep < 4; ++rep) {  // the first repetition warms the caches and is not counted
+            CU(cudaEventRecord(e0, h->stream));
+            if (mode == 0)
+                memory_mix_probe_kernel<false, 4><<<grid, 256, 0, h->stream>>>(h->cmat, h->nphi_hat, c.ind, n, h->Kp, B + 1, sink);
+            else if (mode == 1)
+                memory_mix_probe_kernel<true, 4><<<grid, 256, 0, h->stream>>>(h->cmat, h->nphi_hat, c.ind, n, h->Kp, 0, sink);
+            else
+                memory_mix_probe_kernel<true, 4><<<grid, 256, 0, h->stream>>>(h->cmat, h->nphi_hat, c.ind, n, h->Kp, B + 1, sink);
+            KCHECK();
+            CU(cudaEventRecord(e1, h->stream));
+            CU(cudaEventSynchronize(e1));
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, e0, e1));
+            if (rep > 0 && (best == 0.f || ms < best)) best = ms;
+        }
+        if (out) *out = best;
+        return 0;
+    };
+    int rc = best_of(0, gather_ms);
+    if (!rc) rc = best_of(1, red_ms);
+    if (!rc) rc = best_of(2, mix_ms);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    dfree(h, &sink);
+    return rc;
 }
 
 int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks, int32_t *peer_memory_path) {

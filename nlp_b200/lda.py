@@ -111,7 +111,7 @@ class LatentDirichletAllocation:
         self.Rnd = rand.New(rand.NewSource(time.time_ns() & 0xFFFFFFFFFFFFFFFF))
         # Processes (lda.go:134) = minibatches in flight per step.  Default as in lda.go:185 -- runtime.GOMAXPROCS(0), the
         # host's hardware threads -- and at least one per GPU of the torch.distributed job; the GPUs share them
-        # (Processes / GPUs consecutive minibatches per launch, at most 16).  Processes = 1 is the deterministic parity mode.
+        # (Processes / GPUs consecutive minibatches per launch, at most 256).  Processes = 1 is the deterministic parity mode.
         import os
         self.Processes = max(_world()[1], os.cpu_count() or 1)
         # --- not in the reference ---

@@ -358,6 +358,14 @@ static void *worker_main(void *p) {
     return NULL;
 }
 
+/* SyncGroup: the E-steps of one group read the same nPhi/nZ snapshot and write disjoint documents / private
+ * statistics, so they may run on separate host threads without changing any value */
+static void *estep_main(void *p) {
+    worker_arg *a = (worker_arg *)p;
+    estep_mini_batch(a->l, a->mb, a->wc, a->nTheta, a->m);
+    return NULL;
+}
+
 static void trace_push(oracle_lda *l, double v) {
     if (l->perpTraceLen == l->perpTraceCap) {
         l->perpTraceCap = l->perpTraceCap ? 2 * l->perpTraceCap : 64;
@@ -432,8 +440,12 @@ int oracle_lda_fit_transform(oracle_lda *l, const oracle_csc *m, const double *n
                     mini_batch_reset(mb, K, l->w);
                     mb->start = j * l->BatchSize;
                     mb->end = j < numMiniBatches - 1 ? mb->start + l->BatchSize : c;
-                    estep_mini_batch(l, mb, wc, nTheta, m);
+                    args[g] = (worker_arg){l, mb, m, wc, nTheta, numMiniBatches, &next, &chan};
+                    if (n > 1) pthread_create(&threads[g], NULL, estep_main, &args[g]);
+                    else estep_main(&args[g]);
                 }
+                if (n > 1)
+                    for (int64_t g = 0; g < n; g++) pthread_join(threads[g], NULL);
                 for (int64_t g = 0; g < n; g++) blend_mini_batch(l, &miniBatches[g]);
             }
         } else

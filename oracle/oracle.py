@@ -148,9 +148,12 @@ class LatentDirichletAllocation:
         object.__setattr__(self, "_h", lib().oracle_lda_new(k, seed, processes))
 
     def __del__(self):
-        if getattr(self, "_h", None):
-            lib().oracle_lda_free(self._h)
-            object.__setattr__(self, "_h", None)
+        try:
+            if getattr(self, "_h", None):
+                lib().oracle_lda_free(self._h)
+                object.__setattr__(self, "_h", None)
+        except Exception:   # interpreter shutdown: module globals are already gone
+            pass
 
     def __getattr__(self, name):
         if name in _FIELDS or name in ("w", "d", "iterationsRun", "tokenVisits"):

@@ -200,7 +200,7 @@ def test_bench_reference_arm_prints_one_json_line():
     import subprocess
     import sys
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1",
-                        "--steps", "1", "--warmup", "0", "--cpu-docs-per-worker", "64"], capture_output=True, text=True,
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True,
                        timeout=300)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [x for x in r.stdout.splitlines() if x.strip()]
@@ -211,6 +211,13 @@ def test_bench_reference_arm_prints_one_json_line():
         assert key in j, key
     assert j["impl"] == "reference" and j["cpu_baseline"]["kind"] == "port" and j["value"] > 0
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
+    # the reference arm runs on the CUDA arm's config: same dict, built by the same function
+    sys.path.insert(0, ROOT)
+    import bench
+    sys.argv = ["bench.py", "--workload", "C1"]
+    a = bench.parse()
+    assert j["config"] == bench.common_config(a, *bench.workload(a))
+    assert j["config"]["batch_size"] == 100 and "BatchSize 100" in j["cpu_baseline"]["sample"]
 
 
 def test_bench_cuda_arm_refuses_to_run_without_a_gpu():

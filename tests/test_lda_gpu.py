@@ -139,10 +139,10 @@ def test_topic_widths(k, D, W, b):
 @pytest.mark.parametrize("k,procs,b,D", [(12, 3, 40, 410), (256, 4, 64, 300), (100, 16, 16, 200), (8, 40, 10, 95)])
 def test_processes_concurrent_minibatches(k, procs, b, D):
     """Processes = P on one GPU: P minibatches per launch from one nPhi snapshot, blended in index order -- the
-    oracle's SyncGroup = P restatement of lda.go:487-528 (at most 16 per launch)."""
+    oracle's SyncGroup = P restatement of lda.go:487-528 (at most 256 per launch)."""
     m = synth(D, 500, 30, block=b)
     f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=4, BatchSize=b)
-    o = new_oracle(k, SyncGroup=min(procs, 16), **f)
+    o = new_oracle(k, SyncGroup=min(procs, 256), **f)
     want = o.FitTransform(tuple(m))
     lda = new_lda(k, Processes=procs, **f)
     got = lda.FitTransform(m)
@@ -706,3 +706,23 @@ def test_config3_properties_full_size():
 def test_config4_properties_full_size():
     """configs[3] at full size: 200k docs x 100k vocab, K=1024 (nPhi 410 MB, beyond L2)"""
     _full_size_properties("C4", 2048, 4, 20)  # 25 M-steps per iteration: past the initial transient by iteration 20
+
+
+def test_step_issued_as_sub_range_launches(monkeypatch):
+    """A step whose launch range exceeds LDA_B200_SUB_RANGE_DOCS documents is tiled into sub-ranges: one launch over all
+    of them in the middle iterations, one launch per sub-range in the first iteration (word ids still streaming in) and
+    in the last one (doc-topic rows streaming out to a page-locked result).  Same model as the oracle's SyncGroup."""
+    import torch
+    monkeypatch.setenv("LDA_B200_SUB_RANGE_DOCS", "100")
+    for k, b, procs, D in [(256, 50, 8, 1037), (12, 30, 16, 1000)]:
+        m = synth(D, 700, 30, block=b)
+        f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=3, BatchSize=b)
+        o = new_oracle(k, SyncGroup=procs, **f)
+        want = o.FitTransform(tuple(m))
+        lda = new_lda(k, Processes=procs, **f)
+        out = torch.empty((k, D), dtype=torch.float64).pin_memory()
+        got = lda.FitTransform(m, out=out.numpy())
+        np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+        assert np.abs(got - want).max() <= THETA_ATOL
+        lda2 = new_lda(k, Processes=procs, **f)                       # pageable result: no streaming out, same answer
+        assert np.abs(lda2.FitTransform(m) - want).max() <= THETA_ATOL
