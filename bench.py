@@ -337,6 +337,8 @@ def ours(args):
     L.lda_b200_last_kernel_time(h, C.byref(mb_ms), C.byref(mb_n), C.byref(bl_ms), C.byref(bl_n))
     ar_ms, ar_n = C.c_float(), C.c_int32()
     L.lda_b200_last_allreduce_time(h, C.byref(ar_ms), C.byref(ar_n))
+    phases = (C.c_float * 4)()
+    L.lda_b200_last_exchange_phases(h, phases)
     L.lda_b200_set_profiling(h, 0)
     kernel_ms_max, kernel_ms_min = allmax(mb_ms.value), -allmax(-mb_ms.value)
     ms = allmax(dev_ms)
@@ -390,6 +392,10 @@ def ours(args):
         "exchange": {"path": "peer-memory reduce + M-step kernel (CUDA IPC over NVLink)" if peer else
                      ("ncclAllReduce + blend kernel" if world > 1 else "none (1 GPU)"), "calls": ar_n.value,
                      "avg_ms_incl_wait_for_slowest_rank": (ar_ms.value / ar_n.value) if ar_n.value else None,
+                     "phases_ms_per_step_rank0": dict(zip(
+                         ("opening_barrier_wait_for_slowest_rank", "reduce_blend_over_peer_memory",
+                          "column_sums_closing_barrier_nz", "refresh_c"),
+                         [x / max(ar_n.value, 1) for x in phases])) if peer else None,
                      "bytes": 4 * K * W, "minibatch_kernel_ms_per_launch_rank_min_max": [
                          kernel_ms_min / max(mb_n.value, 1), kernel_ms_max / max(mb_n.value, 1)]},
     }

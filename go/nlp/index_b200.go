@@ -162,8 +162,10 @@ func (b *B200LinearScanIndex) IndexTransform(lda *LatentDirichletAllocation, m m
 
 // Search is index.go:85-115; the matches come nearest first (the reference returns them in heap order).
 func (b *B200LinearScanIndex) Search(qv mat.Vector, k int) []Match {
-	b.lock.RLock()
-	defer b.lock.RUnlock()
+	// The engine behind the handle is not re-entrant (one stream, shared timing events and error text), so searches are
+	// serialised as well: the write lock, where index.go:90 takes the read lock.
+	b.lock.Lock()
+	defer b.lock.Unlock()
 	q := dense(qv)
 	ids := make([]C.int64_t, k)
 	dist := make([]C.double, k)

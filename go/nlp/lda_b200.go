@@ -23,6 +23,7 @@ import "C"
 import (
 	"encoding/binary"
 	"errors"
+	"io"
 	"runtime"
 	"time"
 	"unsafe"
@@ -60,14 +61,20 @@ type LatentDirichletAllocation struct {
 
 	rhoPhiT, rhoThetaT, wordsInCorpus float64 // lda.go:117-120
 	w, d                              int
-	src                               *rand.PCGSource
-	h                                 *C.lda_b200_handle
+	// own is the generator the constructor installed and src its PCG source.  While Rnd == own the initial nPhi / nTheta
+	// are drawn on the device from src's 128-bit state (bit-identical to Rnd.Int() % n, state advanced accordingly).  A
+	// caller who assigns Rnd (lda_test.go:68: lda.Rnd = rand.New(rand.NewSource(0))) gets the draws made in Go from that
+	// generator, in the reference's order, and handed to the library as explicit initial values.
+	own *rand.Rand
+	src *rand.PCGSource
+	h   *C.lda_b200_handle
 }
 
 // NewLatentDirichletAllocation mirrors lda.go:145-189.
 func NewLatentDirichletAllocation(k int) *LatentDirichletAllocation {
 	src := &rand.PCGSource{}
 	src.Seed(uint64(time.Now().UnixNano()))
+	own := rand.New(src)
 	l := &LatentDirichletAllocation{
 		Iterations: 1000, PerplexityTolerance: 1e-2, PerplexityEvaluationFrequency: 30, BatchSize: 100, K: k,
 		BurnInPasses: 1, TransformationPasses: 500, MeanChangeTolerance: 1e-5, ChangeEvaluationFrequency: 30,
@@ -75,16 +82,12 @@ func NewLatentDirichletAllocation(k int) *LatentDirichletAllocation {
 		RhoPhi:   LearningSchedule{S: 10, Tau: 1000, Kappa: 0.9},
 		RhoTheta: LearningSchedule{S: 1, Tau: 10, Kappa: 0.9},
 		rhoPhiT:  1, rhoThetaT: 1,
-		Rnd: rand.New(src), src: src,
+		Rnd: own, own: own, src: src,
 		Processes: runtime.GOMAXPROCS(0), // lda.go:185
 	}
 	runtime.SetFinalizer(l, (*LatentDirichletAllocation).Close)
 	return l
 }
-
-// SetSource replaces Rnd (lda_test.go:68 does `lda.Rnd = rand.New(rand.NewSource(0))`; the shim needs the PCGSource
-// itself to hand its 128-bit state to the device and to advance it afterwards).
-func (l *LatentDirichletAllocation) SetSource(src *rand.PCGSource) { l.src, l.Rnd = src, rand.New(src) }
 
 func (l *LatentDirichletAllocation) config() C.lda_b200_config {
 	return C.lda_b200_config{
@@ -102,9 +105,7 @@ func (l *LatentDirichletAllocation) config() C.lda_b200_config {
 }
 
 func (l *LatentDirichletAllocation) handle() (*C.lda_b200_handle, error) {
-	runtime.LockOSThread() // cgo calls may hop OS threads; every entry point also sets its own device
-	defer runtime.UnlockOSThread()
-	cfg := l.config()
+	cfg := l.config() // a C struct of scalars: no Go pointers inside
 	if l.h == nil {
 		if rc := C.lda_b200_create(&cfg, C.int32_t(l.Device), &l.h); rc != 0 {
 			return nil, errors.New("nlp: " + C.GoString(C.lda_b200_last_error(nil)))
@@ -132,48 +133,50 @@ func (l *LatentDirichletAllocation) Close() {
 	}
 }
 
-// matrix describes m to the library in the storage it already has, so that ToCSC() (lda.go:464-466) and the dense
-// scan of ColNonZeroElemDo (utils.go:51-57) run on the GPU instead of on one host thread:
+// flatMatrix is m in the storage it already has, as the scalar arguments of the lda_b200_*_flat calls, so that ToCSC()
+// (lda.go:464-466) and the dense scan of ColNonZeroElemDo (utils.go:51-57) run on the GPU instead of on one host thread:
 //   *sparse.CSR (what TfidfTransformer emits, weightings.go:79-95) -> LDA_B200_CSR, zero copy
 //   *sparse.CSC                                                      -> LDA_B200_CSC, zero copy
 //   *mat.Dense with Stride == cols                                  -> LDA_B200_DENSE, zero copy
 //   any other sparse.TypeConverter (DOK, COO, ...)                   -> ToCSC() on the host, then LDA_B200_CSC
 //   any other mat.Matrix                                             -> copied into a dense buffer, LDA_B200_DENSE
-// keep holds the Go slices the descriptor points into; the caller passes it to runtime.KeepAlive after the C call.
-func matrix(m mat.Matrix) (desc C.lda_b200_matrix, keep []interface{}) {
+// cgo's pointer rule: Go memory handed to C must not itself contain Go pointers.  A Go-side lda_b200_matrix filled with
+// slice addresses would break it, which is why the slices travel as separate arguments: each is a pointer to a flat
+// []int / []float64.  The library copies to the device during the call and keeps nothing.
+type flatMatrix struct {
+	format     C.int32_t
+	rows, cols C.int64_t
+	ptr, ind   []int // Go int == int64 on the 64-bit platforms the library supports
+	data       []float64
+}
+
+func flatten(m mat.Matrix) flatMatrix {
 	r, c := m.Dims()
-	desc.rows, desc.cols = C.int64_t(r), C.int64_t(c)
-	sparseDesc := func(format C.int32_t, indptr, ind []int, data []float64) {
-		desc.format = format
-		desc.ptr, desc.ind, desc.data = ptrI(indptr), ptrI(ind), ptrF(data) // Go int == int64 on amd64
-		keep = []interface{}{indptr, ind, data}
-	}
+	f := flatMatrix{rows: C.int64_t(r), cols: C.int64_t(c)}
 	switch t := m.(type) {
 	case *sparse.CSR:
 		raw := t.RawMatrix()
-		sparseDesc(C.LDA_B200_CSR, raw.Indptr, raw.Ind, raw.Data)
+		f.format, f.ptr, f.ind, f.data = C.LDA_B200_CSR, raw.Indptr, raw.Ind, raw.Data
 	case *sparse.CSC:
 		raw := t.RawMatrix()
-		sparseDesc(C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data)
+		f.format, f.ptr, f.ind, f.data = C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data
 	case sparse.TypeConverter:
 		raw := t.ToCSC().RawMatrix()
-		sparseDesc(C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data)
+		f.format, f.ptr, f.ind, f.data = C.LDA_B200_CSC, raw.Indptr, raw.Ind, raw.Data
 	default:
-		var data []float64
+		f.format = C.LDA_B200_DENSE
 		if d, ok := m.(*mat.Dense); ok && d.RawMatrix().Stride == c {
-			data = d.RawMatrix().Data
+			f.data = d.RawMatrix().Data
 		} else {
-			data = make([]float64, r*c)
+			f.data = make([]float64, r*c)
 			for i := 0; i < r; i++ {
 				for j := 0; j < c; j++ {
-					data[i*c+j] = m.At(i, j)
+					f.data[i*c+j] = m.At(i, j)
 				}
 			}
 		}
-		desc.format, desc.data = C.LDA_B200_DENSE, ptrF(data)
-		keep = []interface{}{data}
 	}
-	return
+	return f
 }
 
 func ptrI(s []int) *C.int64_t {
@@ -201,6 +204,28 @@ func (l *LatentDirichletAllocation) takePcg(p C.lda_b200_pcg) {
 	_ = l.src.UnmarshalBinary(b[:])
 }
 
+// draws returns rows*K initial values float64(Rnd.Int() % (rows*K)) / float64(rows*K), row-major -- the loops of
+// lda.go:199-205 (nPhi), :472-475 (nTheta) and :422-426 (Transform) -- when the caller has replaced Rnd, nil otherwise
+// (the library then draws on the device from the shim-owned source).
+func (l *LatentDirichletAllocation) draws(rows int) []float64 {
+	if l.Rnd == l.own {
+		return nil
+	}
+	n := rows * l.K
+	out := make([]float64, n)
+	for i := range out {
+		out[i] = float64(l.Rnd.Int()%n) / float64(n)
+	}
+	return out
+}
+
+func (l *LatentDirichletAllocation) counters() C.lda_b200_counters {
+	return C.lda_b200_counters{rho_phi_t: C.double(l.rhoPhiT), rho_theta_t: C.double(l.rhoThetaT), words_in_corpus: C.double(l.wordsInCorpus)}
+}
+func (l *LatentDirichletAllocation) takeCounters(c C.lda_b200_counters) {
+	l.rhoPhiT, l.rhoThetaT, l.wordsInCorpus = float64(c.rho_phi_t), float64(c.rho_theta_t), float64(c.words_in_corpus)
+}
+
 // Fit is lda.go:211-214.
 func (l *LatentDirichletAllocation) Fit(m mat.Matrix) Transformer {
 	if _, err := l.fit(m, false); err != nil {
@@ -217,26 +242,69 @@ func (l *LatentDirichletAllocation) fit(m mat.Matrix, want bool) (mat.Matrix, er
 	if err != nil {
 		return nil, err
 	}
-	desc, keep := matrix(m)
+	f := flatten(m)
 	r, c := m.Dims()
 	l.w, l.d = r, c
 	var theta []float64
 	if want {
 		theta = make([]float64, l.K*c)
 	}
-	ctr := C.lda_b200_counters{rho_phi_t: C.double(l.rhoPhiT), rho_theta_t: C.double(l.rhoThetaT), words_in_corpus: C.double(l.wordsInCorpus)}
+	nphi0 := l.draws(r)   // lda.go:199-205 (init), before ...
+	ntheta0 := l.draws(c) // ... lda.go:472-475
+	ctr := l.counters()
 	rnd := l.pcg()
-	rc := C.lda_b200_fit_matrix(h, &desc, nil, nil, &rnd, &ctr, ptrF(theta), nil, 0, nil, nil)
-	runtime.KeepAlive(keep)
+	rc := C.lda_b200_fit_flat(h, f.format, f.rows, f.cols, ptrI(f.ptr), ptrI(f.ind), ptrF(f.data), ptrF(nphi0), ptrF(ntheta0),
+		&rnd, &ctr, ptrF(theta), nil, 0, nil, nil)
+	runtime.KeepAlive(f)
+	runtime.KeepAlive(nphi0)
+	runtime.KeepAlive(ntheta0)
 	if rc != 0 {
 		return nil, l.err()
 	}
-	l.takePcg(rnd)
-	l.rhoPhiT, l.rhoThetaT, l.wordsInCorpus = float64(ctr.rho_phi_t), float64(ctr.rho_theta_t), float64(ctr.words_in_corpus)
+	l.takePcg(rnd) // unchanged by the library when explicit initial values were given
+	l.takeCounters(ctr)
 	if !want {
 		return nil, nil
 	}
 	return mat.NewDense(l.K, c, theta), nil
+}
+
+// PartialFit is OnlineTransformer.PartialFit (vectorisers.go:36-39; a TODO for LDA at lda.go:147): one SCVB0 iteration
+// over the documents of m, continuing from the current model (a fresh random model on first use).
+func (l *LatentDirichletAllocation) PartialFit(m mat.Matrix) OnlineTransformer {
+	h, err := l.handle()
+	if err != nil {
+		panic(err)
+	}
+	f := flatten(m)
+	r, c := m.Dims()
+	if l.Rnd != l.own && l.w == 0 {
+		// a first PartialFit also initialises nPhi (lda.go:199-205); with a caller-owned Rnd the draws are made here
+		// and installed as the model state before the streaming step
+		nphi0 := l.draws(r)
+		nz := make([]float64, l.K)
+		for i := 0; i < r; i++ {
+			for k := 0; k < l.K; k++ {
+				nz[k] += nphi0[i*l.K+k] // lda.go:203
+			}
+		}
+		if rc := C.lda_b200_set_state(h, C.int64_t(r), ptrF(nphi0), ptrF(nz)); rc != 0 {
+			panic(l.err())
+		}
+	}
+	l.w, l.d = r, c
+	ntheta0 := l.draws(c)
+	ctr := l.counters()
+	rnd := l.pcg()
+	rc := C.lda_b200_partial_fit_flat(h, f.format, f.rows, f.cols, ptrI(f.ptr), ptrI(f.ind), ptrF(f.data), ptrF(ntheta0), &rnd, &ctr, 1, nil)
+	runtime.KeepAlive(f)
+	runtime.KeepAlive(ntheta0)
+	if rc != 0 {
+		panic(l.err())
+	}
+	l.takePcg(rnd)
+	l.takeCounters(ctr)
+	return l
 }
 
 // Transform is lda.go:446-453.
@@ -245,12 +313,15 @@ func (l *LatentDirichletAllocation) Transform(m mat.Matrix) (mat.Matrix, error) 
 	if err != nil {
 		return nil, err
 	}
-	desc, keep := matrix(m)
+	f := flatten(m)
 	_, c := m.Dims()
 	theta := make([]float64, l.K*c)
+	theta0 := l.draws(c) // lda.go:422-426
 	rnd := l.pcg()
-	rc := C.lda_b200_transform_matrix(h, &desc, nil, &rnd, C.double(l.rhoThetaT), ptrF(theta), nil)
-	runtime.KeepAlive(keep)
+	rc := C.lda_b200_transform_flat(h, f.format, f.rows, f.cols, ptrI(f.ptr), ptrI(f.ind), ptrF(f.data), ptrF(theta0), &rnd,
+		C.double(l.rhoThetaT), ptrF(theta), nil)
+	runtime.KeepAlive(f)
+	runtime.KeepAlive(theta0)
 	if rc != 0 {
 		return nil, l.err()
 	}
@@ -264,11 +335,15 @@ func (l *LatentDirichletAllocation) Perplexity(m mat.Matrix) float64 {
 	if err != nil {
 		panic(err)
 	}
-	desc, keep := matrix(m)
+	f := flatten(m)
+	_, c := m.Dims()
+	theta0 := l.draws(c)
 	rnd := l.pcg()
 	var out C.double
-	rc := C.lda_b200_perplexity_matrix(h, &desc, nil, &rnd, C.double(l.rhoThetaT), &out)
-	runtime.KeepAlive(keep)
+	rc := C.lda_b200_perplexity_flat(h, f.format, f.rows, f.cols, ptrI(f.ptr), ptrI(f.ind), ptrF(f.data), ptrF(theta0), &rnd,
+		C.double(l.rhoThetaT), &out)
+	runtime.KeepAlive(f)
+	runtime.KeepAlive(theta0)
 	if rc != 0 {
 		panic(l.err())
 	}
@@ -287,4 +362,51 @@ func (l *LatentDirichletAllocation) Components() mat.Matrix {
 		panic(l.err())
 	}
 	return mat.NewDense(l.K, l.w, out)
+}
+
+// Save binary serialises the model and writes it into w, in the style of TfidfTransformer.Save (weightings.go:97-101)
+// and TruncatedSVD.Save (dimreduction.go:111-121): K, the private counters, nPhi and nZ as gonum MarshalBinaryTo
+// records.  The bytes are produced by the library (lda_b200_save), so every host language writes the same file.
+func (l *LatentDirichletAllocation) Save(w io.Writer) error {
+	h, err := l.handle()
+	if err != nil {
+		return err
+	}
+	var n C.int64_t
+	if rc := C.lda_b200_save_size(h, &n); rc != 0 {
+		return errors.New("nlp: no model to save")
+	}
+	buf := make([]byte, int(n))
+	ctr := l.counters()
+	if rc := C.lda_b200_save(h, &ctr, unsafe.Pointer(&buf[0]), n, &n); rc != 0 {
+		return l.err()
+	}
+	_, err = w.Write(buf[:int(n)])
+	return err
+}
+
+// Load binary deserialises a model written by Save into the receiver (dimreduction.go:127-153).  Load should only be
+// performed with trusted data.
+func (l *LatentDirichletAllocation) Load(r io.Reader) error {
+	buf, err := io.ReadAll(r)
+	if err != nil {
+		return err
+	}
+	if len(buf) < 8 {
+		return io.ErrUnexpectedEOF
+	}
+	h, err := l.handle()
+	if err != nil {
+		return err
+	}
+	var ctr C.lda_b200_counters
+	if rc := C.lda_b200_load(h, unsafe.Pointer(&buf[0]), C.int64_t(len(buf)), &ctr); rc != 0 {
+		return l.err()
+	}
+	var w C.int64_t
+	var k C.int32_t
+	C.lda_b200_get_dims(h, &w, &k)
+	l.K, l.w = int(k), int(w)
+	l.takeCounters(ctr)
+	return nil
 }

@@ -187,6 +187,23 @@ int lda_b200_transform_matrix(lda_b200_handle *h, const lda_b200_matrix *m, cons
 int lda_b200_perplexity_matrix(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
                                double rho_theta_t, double *out);
 
+/* The same calls once more with the matrix descriptor spread over scalar arguments: format, rows, cols, ptr, ind, data
+ * are the fields of lda_b200_matrix.  This is the form a cgo caller uses -- cgo forbids passing a pointer to Go memory
+ * that itself holds Go pointers (a Go-side lda_b200_matrix filled with slice addresses), while every argument here is
+ * a plain pointer to a flat slice or a scalar.  go/nlp/lda_b200.go binds exactly these. */
+int lda_b200_fit_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr, const int64_t *ind,
+                      const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                      double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals, int32_t *iters_run);
+int lda_b200_partial_fit_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                              const int64_t *ind, const double *data, const double *ntheta0, lda_b200_pcg *rnd,
+                              lda_b200_counters *ctr, int32_t iterations, double *theta_out);
+int lda_b200_transform_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                            const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                            double rho_theta_t, double *theta_out, int32_t *passes_out);
+int lda_b200_perplexity_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                             const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                             double rho_theta_t, double *out);
+
 /* Components, lda.go:414-416: out = K*W doubles */
 int lda_b200_components(lda_b200_handle *h, double *out);
 
@@ -195,6 +212,21 @@ int lda_b200_components(lda_b200_handle *h, double *out);
 int lda_b200_get_dims(const lda_b200_handle *h, int64_t *W, int32_t *K);
 int lda_b200_get_state(lda_b200_handle *h, double *nphi, double *nz);
 int lda_b200_set_state(lda_b200_handle *h, int64_t W, const double *nphi, const double *nz);
+
+/* Save / Load in the library's binary style (TfidfTransformer weightings.go:97-116, TruncatedSVD dimreduction.go:111-153:
+ * little-endian scalars followed by gonum `MarshalBinaryTo` records).  Layout of an LDA model, all little endian:
+ *     uint64  K
+ *     float64 rhoPhiT, rhoThetaT, wordsInCorpus                       (the private counters, lda.go:117-120)
+ *     mat.Dense record of nPhi (W x K, [w*K+k]) , mat.Dense record of nZ (1 x K)
+ * where a mat.Dense record is gonum mat/io.go's storage header -- uint32 version 0xFE000001, bytes 'G','F','A', bool unit
+ * = 0, int64 rows, cols, ku = 0, kl = 0 (40 bytes) -- followed by rows*cols float64 in row-major order.
+ * lda_b200_save_size gives the byte count; lda_b200_save writes exactly that many bytes into buf (cap >= size);
+ * lda_b200_load replaces the handle's model and configuration K by the file's and returns the counters.
+ * (The reference has no LDA Save/Load and no gonum-produced bytes are available offline: the record layout follows
+ * gonum's documented storage header; see DESIGN.md "parity unpinned" note.) */
+int lda_b200_save_size(const lda_b200_handle *h, int64_t *bytes);
+int lda_b200_save(lda_b200_handle *h, const lda_b200_counters *ctr, void *buf, int64_t cap, int64_t *written);
+int lda_b200_load(lda_b200_handle *h, const void *buf, int64_t len, lda_b200_counters *ctr);
 
 /* host-side restatement of Rnd.Int() % n draws (lda.go:201,425,474) for callers without
  * golang.org/x/exp/rand: out[i] = float64(Int() % n) / float64(n); advances *rnd. */
@@ -264,6 +296,11 @@ int lda_b200_probe_memory_mix(lda_b200_handle *h, int64_t *entries, float *gathe
 int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks, int32_t *peer_memory_path);
 /* same for the per-step all-reduce (multi-GPU); the time includes waiting for the slowest rank's kernel */
 int lda_b200_last_allreduce_time(const lda_b200_handle *h, float *allreduce_ms, int32_t *allreduce_calls);
+
+/* phases of the peer-memory exchange during the last profiled lda_b200_fit_iterate call, total ms each: [0] opening
+ * barrier (the wait for the slowest rank's minibatch kernel), [1] reduce + blend kernel over peer memory, [2] column
+ * sums + closing barrier + nZ, [3] refresh of C */
+int lda_b200_last_exchange_phases(const lda_b200_handle *h, float *phase_ms4);
 
 #ifdef __cplusplus
 }

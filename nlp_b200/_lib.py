@@ -61,6 +61,16 @@ SYMBOLS = {
     "lda_b200_partial_fit_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.POINTER(Counters), C.c_int32, _P]),
     "lda_b200_transform_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.c_double, _P, _P]),
     "lda_b200_perplexity_matrix": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.c_double, C.POINTER(C.c_double)]),
+    "lda_b200_fit_flat": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(Pcg), C.POINTER(Counters),
+                                    _P, _P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "lda_b200_partial_fit_flat": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg),
+                                            C.POINTER(Counters), C.c_int32, _P]),
+    "lda_b200_transform_flat": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double, _P, _P]),
+    "lda_b200_perplexity_flat": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg), C.c_double,
+                                           C.POINTER(C.c_double)]),
+    "lda_b200_save_size": (C.c_int, [_P, C.POINTER(C.c_int64)]),
+    "lda_b200_save": (C.c_int, [_P, C.POINTER(Counters), _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "lda_b200_load": (C.c_int, [_P, _P, C.c_int64, C.POINTER(Counters)]),
     "lda_b200_components": (C.c_int, [_P, _P]),
     "lda_b200_get_dims": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "lda_b200_get_state": (C.c_int, [_P, _P, _P]),
@@ -84,6 +94,7 @@ SYMBOLS = {
                                             C.POINTER(C.c_int32)]),
     "lda_b200_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "lda_b200_last_allreduce_time": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
+    "lda_b200_last_exchange_phases": (C.c_int, [_P, C.POINTER(C.c_float)]),
     "lda_b200_probe_memory_mix": (C.c_int, [_P, C.POINTER(C.c_int64), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                             C.POINTER(C.c_float)]),
 }

@@ -101,14 +101,24 @@ int reserve(lda_b200_index *ix, int64_t extra) {
     const int64_t ncap = (std::max<int64_t>({ix->cap * 2, ix->n + extra, 1024}) + MMA_TV - 1) / MMA_TV * MMA_TV;
     double *nvec = nullptr, *nnorm = nullptr;
     int64_t *nids = nullptr;
-    ITRY(ialloc(ix, &nvec, (size_t)ix->dim * ncap));
-    ITRY(ialloc(ix, &nnorm, (size_t)ncap));
-    ITRY(ialloc(ix, &nids, (size_t)ncap));
-    if (ix->n > 0) {
-        ICU(cudaMemcpy2DAsync(nvec, (size_t)ncap * 8, ix->vec, (size_t)ix->cap * 8, (size_t)ix->n * 8, (size_t)ix->dim,
-                              cudaMemcpyDeviceToDevice, ix->stream));
-        ICU(cudaMemcpyAsync(nnorm, ix->norm, (size_t)ix->n * 8, cudaMemcpyDeviceToDevice, ix->stream));
-        ICU(cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * 8, cudaMemcpyDeviceToDevice, ix->stream));
+    auto grow = [&]() -> int {
+        ITRY(ialloc(ix, &nvec, (size_t)ix->dim * ncap));
+        ITRY(ialloc(ix, &nnorm, (size_t)ncap));
+        ITRY(ialloc(ix, &nids, (size_t)ncap));
+        if (ix->n > 0) {
+            ICU(cudaMemcpy2DAsync(nvec, (size_t)ncap * 8, ix->vec, (size_t)ix->cap * 8, (size_t)ix->n * 8, (size_t)ix->dim,
+                                  cudaMemcpyDeviceToDevice, ix->stream));
+            ICU(cudaMemcpyAsync(nnorm, ix->norm, (size_t)ix->n * 8, cudaMemcpyDeviceToDevice, ix->stream));
+            ICU(cudaMemcpyAsync(nids, ix->ids, (size_t)ix->n * 8, cudaMemcpyDeviceToDevice, ix->stream));
+        }
+        return 0;
+    };
+    const int rc = grow();
+    if (rc) {  // the index keeps its old storage; nothing allocated here survives
+        ifree(ix, &nvec);
+        ifree(ix, &nnorm);
+        ifree(ix, &nids);
+        return rc;
     }
     ifree(ix, &ix->vec);
     ifree(ix, &ix->norm);
@@ -176,6 +186,9 @@ int launch_scan(lda_b200_index *ix, const ScanArgs &a, const ScanPlan &pl, int n
 int search_batch(lda_b200_index *ix, const double *d_q, int nb, int k, int64_t *ids_out, double *dist_out, int32_t *found_out) {
     const int64_t n = ix->n;
     const int k_eff = (int)std::min<int64_t>(k, n);
+    // the k survivors of a query are ordered by one thread block (bitonic network over the next power of two)
+    if (k_eff > (1 << 20))
+        return ifail(ix, LDA_B200_EUNSUPPORTED, "k = %d nearest neighbours per query exceeds the supported 2^20", k_eff);
     const ScanPlan pl = plan_scan(ix, nb);
     const int QB = pl.QB;
     const int nchunks = (nb + QB - 1) / QB;
@@ -280,8 +293,15 @@ int index_begin_append(lda_b200_index *ix, int device, int dim, int64_t n, doubl
         return ifail(ix, LDA_B200_EINVAL, "vector has %d elements, the index holds vectors of %d", dim, ix->dim);
     if (ix->n + n >= (1LL << 32) - 1) return ifail(ix, LDA_B200_EUNSUPPORTED, "more than 2^32 - 2 vectors");
     ICU(cudaSetDevice(ix->device));
-    ix->dim = dim;
-    ITRY(reserve(ix, n));
+    {
+        const int32_t old_dim = ix->dim;
+        ix->dim = dim;  // reserve sizes the rows by it
+        const int rc = reserve(ix, n);
+        if (rc) {
+            ix->dim = old_dim;  // a failed first add does not pin the dimension
+            return rc;
+        }
+    }
     ICU(cudaStreamSynchronize(ix->stream));
     *dst = ix->vec + ix->n;
     *ld = ix->cap;
@@ -367,8 +387,15 @@ int lda_b200_index_add(lda_b200_index *ix, int32_t dim, int64_t n, const double 
     if (ix->n + n >= (1LL << 32) - 1) return ifail(ix, LDA_B200_EUNSUPPORTED, "more than 2^32 - 2 vectors");
     if (n == 0) return 0;
     ICU(cudaSetDevice(ix->device));
-    ix->dim = dim;
-    ITRY(reserve(ix, n));
+    {
+        const int32_t old_dim = ix->dim;
+        ix->dim = dim;  // reserve sizes the rows by it
+        const int rc = reserve(ix, n);
+        if (rc) {
+            ix->dim = old_dim;  // a failed first add does not pin the dimension
+            return rc;
+        }
+    }
     ICU(cudaMemcpy2DAsync(ix->vec + ix->n, (size_t)ix->cap * 8, m, (size_t)ld * 8, (size_t)n * 8, (size_t)dim, cudaMemcpyHostToDevice,
                           ix->stream));
     std::vector<int64_t> new_ids((size_t)n);

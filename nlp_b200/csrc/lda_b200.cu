@@ -86,7 +86,9 @@ struct DeviceCSC {
 struct EventPair {
     cudaEvent_t a, b;
     int kind;  // 0 = minibatch kernel, 1 = M-step kernels, 2 = exchange (all-reduce or peer kernel; includes the wait
-               // for the slowest rank)
+               // for the slowest rank); phases of the peer-memory exchange: 3 = opening barrier (= waiting for the slowest
+               // rank's minibatch kernel), 4 = reduce + blend over peer memory, 5 = column sums + closing barrier + nZ,
+               // 6 = refresh of C
 };
 
 }  // namespace
@@ -171,6 +173,7 @@ struct lda_b200_handle {
     size_t ev_used = 0;
     float mb_ms = 0, blend_ms = 0, ar_ms = 0;
     int mb_n = 0, blend_n = 0, ar_n = 0;
+    float phase_ms[4] = {0, 0, 0, 0};  // kinds 3..6
 };
 
 namespace {
@@ -398,7 +401,7 @@ inline int blend_block(int Kp) {
 // ---- profiling events ---------------------------------------------------------------------------------
 int ev_begin(lda_b200_handle *h, int kind, int *slot) {
     *slot = -1;
-    if (!h->profiling || h->ev_used >= 8192) return 0;
+    if (!h->profiling || h->ev_used >= 16384) return 0;
     if (h->ev_used == h->ev_pool.size()) {
         EventPair p;
         CU(cudaEventCreate(&p.a));
@@ -417,6 +420,7 @@ int ev_end(lda_b200_handle *h, int slot) {
 int ev_collect(lda_b200_handle *h) {
     h->mb_ms = h->blend_ms = h->ar_ms = 0;
     h->mb_n = h->blend_n = h->ar_n = 0;
+    for (float &x : h->phase_ms) x = 0;
     for (size_t i = 0; i < h->ev_used; ++i) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, h->ev_pool[i].a, h->ev_pool[i].b));
@@ -426,6 +430,8 @@ int ev_collect(lda_b200_handle *h) {
         } else if (h->ev_pool[i].kind == 1) {
             h->blend_ms += ms;
             h->blend_n++;
+        } else if (h->ev_pool[i].kind >= 3) {
+            h->phase_ms[h->ev_pool[i].kind - 3] += ms;
         } else {
             h->ar_ms += ms;
             h->ar_n++;
@@ -1862,8 +1868,11 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 int slot;
                 TRY(ev_begin(h, 2, &slot));
                 bar.epoch = ++h->epoch;
+                int ph;
+                TRY(ev_begin(h, 3, &ph));
                 xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
                 KCHECK();
+                TRY(ev_end(h, ph));
                 FusedArgs fa;
                 fa.pt = h->peers;
                 fa.cur = h->hat_cur;
@@ -1877,6 +1886,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
                 fa.partials = h->partials;
                 const int bs = blend_block(h->Kp);
+                TRY(ev_begin(h, 4, &ph));
                 if (R <= 2)
                     peer_reduce_blend_kernel<4, 2><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 else if (R <= 4)
@@ -1884,11 +1894,15 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 else
                     peer_reduce_blend_kernel<1, 8><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 KCHECK();
+                TRY(ev_end(h, ph));
+                TRY(ev_begin(h, 5, &ph));
                 TRY(reduce_partials(h, h->sms * 4, h->Kp, h->nzhat, false, h->stream));  // this rank's share of nZHat
                 bar.finish = 1;
                 bar.epoch = ++h->epoch;
                 xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
                 KCHECK();
+                TRY(ev_end(h, ph));
+                TRY(ev_begin(h, 6, &ph));
                 BlendArgs ca;  // c = (nPhi' + eta) invZ' over the local replica
                 ca.nphi = h->nphi;
                 ca.nphi_hat = nullptr;
@@ -1901,6 +1915,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 ca.eta = (float)cfg.eta;
                 phi_blend_kernel<<<h->sms * 4, bs, 0, h->stream>>>(ca);
                 KCHECK();
+                TRY(ev_end(h, ph));
                 TRY(ev_end(h, slot));
                 h->hat_cur ^= 1;
                 h->nphi_hat = h->hat_buf[h->hat_cur];
@@ -2217,6 +2232,146 @@ int lda_b200_set_state(lda_b200_handle *h, int64_t W, const double *nphi, const 
     return 0;
 }
 
+// ---- the *_matrix calls with the descriptor spread over scalar arguments (the form cgo can call) ----------------------
+static lda_b200_matrix flat_matrix(int32_t format, int64_t rows, int64_t cols, const int64_t *ptr, const int64_t *ind, const double *data) {
+    lda_b200_matrix m;
+    memset(&m, 0, sizeof m);
+    m.format = format;
+    m.rows = rows;
+    m.cols = cols;
+    m.ptr = ptr;
+    m.ind = ind;
+    m.data = data;
+    return m;
+}
+
+int lda_b200_fit_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr, const int64_t *ind,
+                      const double *data, const double *nphi0, const double *ntheta0, lda_b200_pcg *rnd, lda_b200_counters *ctr,
+                      double *theta_out, double *perp_trace, int32_t perp_cap, int32_t *n_evals, int32_t *iters_run) {
+    const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
+    return lda_b200_fit_matrix(h, &m, nphi0, ntheta0, rnd, ctr, theta_out, perp_trace, perp_cap, n_evals, iters_run);
+}
+
+int lda_b200_partial_fit_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                              const int64_t *ind, const double *data, const double *ntheta0, lda_b200_pcg *rnd,
+                              lda_b200_counters *ctr, int32_t iterations, double *theta_out) {
+    const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
+    return lda_b200_partial_fit_matrix(h, &m, ntheta0, rnd, ctr, iterations, theta_out);
+}
+
+int lda_b200_transform_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                            const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                            double rho_theta_t, double *theta_out, int32_t *passes_out) {
+    const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
+    return lda_b200_transform_matrix(h, &m, theta0, rnd, rho_theta_t, theta_out, passes_out);
+}
+
+int lda_b200_perplexity_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                             const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                             double rho_theta_t, double *out) {
+    const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
+    return lda_b200_perplexity_matrix(h, &m, theta0, rnd, rho_theta_t, out);
+}
+
+// ---- Save / Load (layout in include/lda_b200.h) ---------------------------------------------------------------------
+namespace {
+constexpr uint32_t kGonumVersion = 0xFE000001u;
+constexpr int64_t kDenseHeader = 40;  // uint32 version, 'G','F','A', bool unit, int64 rows, cols, ku, kl
+void put_dense_header(unsigned char *p, int64_t rows, int64_t cols) {
+    memset(p, 0, (size_t)kDenseHeader);
+    memcpy(p, &kGonumVersion, 4);  // the host is little endian (x86-64 / aarch64)
+    p[4] = 'G';
+    p[5] = 'F';
+    p[6] = 'A';
+    p[7] = 0;
+    memcpy(p + 8, &rows, 8);
+    memcpy(p + 16, &cols, 8);
+}
+bool get_dense_header(const unsigned char *p, int64_t *rows, int64_t *cols) {
+    uint32_t v;
+    memcpy(&v, p, 4);
+    if (v != kGonumVersion || p[4] != 'G' || p[5] != 'F' || p[6] != 'A') return false;
+    memcpy(rows, p + 8, 8);
+    memcpy(cols, p + 16, 8);
+    return *rows >= 0 && *cols >= 0;
+}
+}  // namespace
+
+int lda_b200_save_size(const lda_b200_handle *h, int64_t *bytes) {
+    if (!h || !bytes) return LDA_B200_EINVAL;
+    if (!h->fitted) return LDA_B200_ESTATE;
+    *bytes = 32 + kDenseHeader + h->W * h->K * 8 + kDenseHeader + (int64_t)h->K * 8;
+    return 0;
+}
+
+int lda_b200_save(lda_b200_handle *h, const lda_b200_counters *ctr, void *buf, int64_t cap, int64_t *written) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!ctr || !buf) return fail(h, LDA_B200_EINVAL, "counters / buffer is NULL");
+    if (!h->fitted) return fail(h, LDA_B200_ESTATE, "no model state");
+    int64_t need = 0;
+    TRY(lda_b200_save_size(h, &need));
+    if (cap < need) return fail(h, LDA_B200_EINVAL, "buffer of %lld bytes is too small for a model of %lld bytes", (long long)cap, (long long)need);
+    unsigned char *p = (unsigned char *)buf;
+    const uint64_t k = (uint64_t)h->K;
+    memcpy(p, &k, 8);
+    memcpy(p + 8, &ctr->rho_phi_t, 8);
+    memcpy(p + 16, &ctr->rho_theta_t, 8);
+    memcpy(p + 24, &ctr->words_in_corpus, 8);
+    p += 32;
+    put_dense_header(p, h->W, h->K);
+    unsigned char *nphi_at = p + kDenseHeader;
+    p = nphi_at + h->W * h->K * 8;
+    put_dense_header(p, 1, h->K);
+    unsigned char *nz_at = p + kDenseHeader;
+    // the float64 payloads may sit at any byte offset of the caller's buffer: go through aligned temporaries when needed
+    if (((uintptr_t)nphi_at | (uintptr_t)nz_at) % 8 == 0) {
+        TRY(lda_b200_get_state(h, (double *)nphi_at, (double *)nz_at));
+    } else {
+        std::vector<double> a((size_t)(h->W * h->K)), b((size_t)h->K);
+        TRY(lda_b200_get_state(h, a.data(), b.data()));
+        memcpy(nphi_at, a.data(), a.size() * 8);
+        memcpy(nz_at, b.data(), b.size() * 8);
+    }
+    if (written) *written = need;
+    return 0;
+}
+
+int lda_b200_load(lda_b200_handle *h, const void *buf, int64_t len, lda_b200_counters *ctr) {
+    if (!h) return LDA_B200_EINVAL;
+    if (!buf || !ctr) return fail(h, LDA_B200_EINVAL, "buffer / counters is NULL");
+    if (h->fit_open) return fail(h, LDA_B200_ESTATE, "a fit is in progress");
+    const unsigned char *p = (const unsigned char *)buf;
+    if (len < 32 + kDenseHeader) return fail(h, LDA_B200_EINVAL, "unexpected EOF: %lld bytes hold no model", (long long)len);  // io.ErrUnexpectedEOF, dimreduction.go:135
+    uint64_t k;
+    lda_b200_counters c;
+    memcpy(&k, p, 8);
+    memcpy(&c.rho_phi_t, p + 8, 8);
+    memcpy(&c.rho_theta_t, p + 16, 8);
+    memcpy(&c.words_in_corpus, p + 24, 8);
+    int64_t rows = 0, cols = 0;
+    if (!get_dense_header(p + 32, &rows, &cols)) return fail(h, LDA_B200_EINVAL, "not a gonum mat.Dense record (nPhi)");
+    if (k < 1 || k > 1024 || cols != (int64_t)k || rows < 1) return fail(h, LDA_B200_EINVAL, "model dimensions do not match K");
+    const int64_t nphi_off = 32 + kDenseHeader, nz_hdr = nphi_off + rows * cols * 8;
+    if (rows > (len - nphi_off) / (cols * 8) || len < nz_hdr + kDenseHeader + cols * 8)
+        return fail(h, LDA_B200_EINVAL, "unexpected EOF: truncated mat.Dense record");
+    int64_t zr = 0, zc = 0;
+    if (!get_dense_header(p + nz_hdr, &zr, &zc) || zr != 1 || zc != cols) return fail(h, LDA_B200_EINVAL, "not a gonum mat.Dense record (nZ)");
+    lda_b200_config cfg = h->cfg;
+    cfg.K = (int32_t)k;
+    TRY(lda_b200_set_config(h, &cfg));
+    const unsigned char *nphi_at = p + nphi_off, *nz_at = p + nz_hdr + kDenseHeader;
+    if (((uintptr_t)nphi_at | (uintptr_t)nz_at) % 8 == 0) {
+        TRY(lda_b200_set_state(h, rows, (const double *)nphi_at, (const double *)nz_at));
+    } else {
+        std::vector<double> a((size_t)(rows * cols)), b((size_t)cols);
+        memcpy(a.data(), nphi_at, a.size() * 8);
+        memcpy(b.data(), nz_at, b.size() * 8);
+        TRY(lda_b200_set_state(h, rows, a.data(), b.data()));
+    }
+    *ctr = c;
+    return 0;
+}
+
 // ---- host-only planning helpers -----------------------------------------------------------------------------
 int lda_b200_plan_step(const lda_b200_schedule *rho_phi, double rho_phi_t, int32_t n_s, int32_t rank, double *A,
                        double *c_rank) {
@@ -2398,6 +2553,12 @@ int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks,
     if (rank) *rank = h->rank;
     if (nranks) *nranks = h->nranks;
     if (peer_memory_path) *peer_memory_path = h->peer_ok ? 1 : 0;
+    return 0;
+}
+
+int lda_b200_last_exchange_phases(const lda_b200_handle *h, float *phase_ms4) {
+    if (!h || !phase_ms4) return LDA_B200_EINVAL;
+    for (int i = 0; i < 4; ++i) phase_ms4[i] = h->phase_ms[i];
     return 0;
 }
 

@@ -33,6 +33,7 @@ class LinearScanIndex:
         self._auto = []       # (first handle, end handle, first id) of runs with default ids, in insertion order
         self._removed = set() # handles of removed default-id vectors
         self._next = 0
+        self._next_default_id = 0   # default ids are never reused, whatever has been removed since
         self._dim = None      # fixed by the first vector
         h = C.c_void_p()
         _lib.check_index(_lib.lib().lda_b200_index_create(device, compareFN.code, C.byref(h)))
@@ -117,7 +118,7 @@ class LinearScanIndex:
     # ---- batched forms -------------------------------------------------------------------------------------
     def IndexColumns(self, m, ids=None):
         """ColDo(m, func(j, v) { index.Index(v, ids[j]) }): every column of the dim x n matrix m (e.g. the K x D matrix
-        Transform returns), ids default to the column numbers continuing from the current size"""
+        Transform returns), ids default to consecutive numbers continuing from the last default id handed out (never reused after Remove)"""
         m = np.asarray(m, dtype=np.float64)
         if m.ndim != 2:
             raise ValueError("nlp: matrix must be 2-dimensional")
@@ -126,20 +127,21 @@ class LinearScanIndex:
         n = m.shape[1]
         if ids is not None and len(ids) != n:
             raise ValueError("nlp: one id per column")
-        first_id = len(self)
+        first_id = self._next_default_id
         handles = self._new_handles(n)
         _lib.check_index(_lib.lib().lda_b200_index_add(self._h, m.shape[0], n, _ptr(m), max(n, 1), _ptr(handles)), self._h)
         if n:
             self._dim = m.shape[0]
         if ids is None:
             self._register_auto(handles, first_id)
+            self._next_default_id = first_id + n
         else:
             self._register(handles, ids)
 
     def IndexTransform(self, lda, m, ids=None, theta0=None):
         """ColDo(lda.Transform(m), func(j, v) { index.Index(v, ids[j]) }) without the vectors leaving the GPU: the
         Transform pipeline (lda.go:446-453) writes its K x D result straight into this index's storage.  ids default to
-        the column numbers of m."""
+        the column numbers of m, offset by the default ids handed out before (0 on a fresh index)."""
         from .lda import as_matrix
         desc, _rows, cols, _keep = as_matrix(m, lda.DeviceConvert)
         h = lda._handle()
@@ -154,7 +156,8 @@ class LinearScanIndex:
         if cols:
             self._dim = lda.K
         if ids is None:
-            self._register_auto(handles, 0)
+            self._register_auto(handles, self._next_default_id)
+            self._next_default_id += cols
         else:
             self._register(handles, list(ids))
 

@@ -332,15 +332,26 @@ class LatentDirichletAllocation:
     # ---- persistence in the library's binary style (weightings.go:97-116, dimreduction.go:111-153) ---------------
     def Save(self, w):
         """uint64 K, float64 rhoPhiT / rhoThetaT / wordsInCorpus (little endian), then nPhi (W x K) and nZ (1 x K) as
-        gonum `mat.Dense.MarshalBinaryTo` records"""
-        nphi, nz = self.GetState()
-        w.write(serialise_model(self.K, (self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus), nphi, nz))
+        gonum `mat.Dense.MarshalBinaryTo` records.  The bytes are produced by the library (lda_b200_save), so the Go,
+        C++ and Python hosts write the same file; serialise_model below restates the layout for the tests."""
+        h = self._handle()
+        L = _lib.lib()
+        n = C.c_int64(0)
+        _lib.check(L.lda_b200_save_size(h, C.byref(n)), h)
+        buf = np.empty(n.value, dtype=np.uint8)
+        _lib.check(L.lda_b200_save(h, self._counters(), _ptr(buf), n.value, C.byref(n)), h)
+        w.write(buf[:n.value].tobytes())
 
     def Load(self, r):
-        k, ctr, nphi, nz = deserialise_model(r.read())
-        self.K = k
-        self.rhoPhiT, self.rhoThetaT, self.wordsInCorpus = ctr
-        self.SetState(nphi, nz)
+        raw = r.read()
+        if len(raw) < 8:
+            raise ValueError("nlp: unexpected EOF")  # io.ErrUnexpectedEOF in dimreduction.go:135
+        buf = np.frombuffer(raw, dtype=np.uint8)
+        h = self._handle()
+        ctr = self._counters()
+        _lib.check(_lib.lib().lda_b200_load(h, _ptr(buf), buf.size, ctr), h)
+        self.w, self.K = self._dims_raw()
+        self._take(ctr)
         self._has_model = True
 
     def Transform(self, m, theta0=None, return_passes=False):
@@ -370,8 +381,12 @@ class LatentDirichletAllocation:
         return out.value
 
     def _dims(self):
+        self._handle()
+        return self._dims_raw()
+
+    def _dims_raw(self):
         w, k = C.c_int64(0), C.c_int32(0)
-        _lib.check(_lib.lib().lda_b200_get_dims(self._handle(), C.byref(w), C.byref(k)), self._h)
+        _lib.check(_lib.lib().lda_b200_get_dims(self._h, C.byref(w), C.byref(k)), self._h)
         return int(w.value), int(k.value)
 
     def Components(self):

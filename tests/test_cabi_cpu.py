@@ -266,3 +266,20 @@ def test_pairwise_comparers_name_the_reference_functions():
         assert int(enum[snake]) == c.code, c.name
     with pytest.raises(TypeError):
         nlp_b200.NewLinearScanIndex(lambda a, b: 0.0)
+
+
+def test_model_file_fixture_layout():
+    """tests/golden/lda_model_k3_w9.bin (tests/golden/make_model_fixture.py): the bytes of the model file format, field by
+    field, and the Python restatement of the writer reproduces them"""
+    import struct
+    from nlp_b200.lda import deserialise_model, serialise_model
+    from tests.golden import make_model_fixture as F
+    raw = open(os.path.join(ROOT, "tests", "golden", "lda_model_k3_w9.bin"), "rb").read()
+    assert raw == F.model_bytes() and len(raw) == 32 + 40 + 27 * 8 + 40 + 3 * 8
+    assert struct.unpack_from("<Qddd", raw, 0) == (3, 5.0, 37.0, 1234.0)
+    assert struct.unpack_from("<IBBBBqqqq", raw, 32) == (0xFE000001, ord("G"), ord("F"), ord("A"), 0, 9, 3, 0, 0)
+    assert struct.unpack_from("<IBBBBqqqq", raw, 32 + 40 + 27 * 8) == (0xFE000001, ord("G"), ord("F"), ord("A"), 0, 1, 3, 0, 0)
+    nphi, nz = F.arrays()
+    assert serialise_model(3, F.COUNTERS, nphi, nz) == raw
+    k, ctr, a, b = deserialise_model(raw)
+    assert k == 3 and ctr == F.COUNTERS and np.array_equal(a, nphi) and np.array_equal(b, nz)

@@ -10,11 +10,14 @@ EXE = os.path.join(ROOT, "tests", "cpp", "lda_test")
 
 
 def build(name="lda_test"):
-    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
     exe = os.path.join(ROOT, "tests", "cpp", name)
     libdir = os.path.join(ROOT, "nlp_b200")
-    cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
-           "-L", libdir, "-llda_b200", "-Wl,-rpath," + libdir]
+    if os.path.exists(os.path.join(ROOT, "tests", "cpp", name + ".c")):   # plain C: what cgo compiles the header as
+        cmd = ["gcc", "-std=c11", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "tests", "cpp", name + ".c"), "-o", exe, "-L", libdir, "-llda_b200", "-lm", "-Wl,-rpath," + libdir]
+    else:
+        cmd = ["g++", "-std=c++17", "-O2", "-Wall", "-Wextra", "-I", os.path.join(ROOT, "include"),
+               os.path.join(ROOT, "tests", "cpp", name + ".cpp"), "-o", exe, "-L", libdir, "-llda_b200", "-Wl,-rpath," + libdir]
     subprocess.check_call(cmd)
     return exe
 
@@ -22,6 +25,7 @@ def build(name="lda_test"):
 def test_cpp_host_mirror_compiles_and_links():
     assert os.path.exists(build())
     assert os.path.exists(build("index_test"))
+    assert os.path.exists(build("go_shim_sequence_test"))
 
 
 def test_cpp_host_fails_loudly_without_gpu():
@@ -44,5 +48,15 @@ def test_reference_tests_in_cpp():
 @pytest.mark.gpu
 def test_reference_index_tests_in_cpp():
     r = subprocess.run([build("index_test")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "PASS" in r.stdout
+
+
+@pytest.mark.gpu
+def test_go_shim_call_sequence_in_c():
+    """go/nlp/lda_b200.go cannot be compiled here (no Go toolchain): its call sequence -- flat-argument entry points,
+    malloc'ed pageable buffers, host-side draws for a caller-assigned Rnd, PartialFit, Save / Load -- replayed from plain C
+    with lda_test.go's three tests on top"""
+    r = subprocess.run([build("go_shim_sequence_test")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "PASS" in r.stdout

@@ -320,6 +320,28 @@ def test_partial_fit_and_persistence(tmp_path):
     lda2.Rnd.src.state = lda.Rnd.src.state
     assert np.array_equal(lda.Transform(held), lda2.Transform(held))
     assert np.array_equal(lda.Components(), lda2.Components())
+    # the file is written by the library (lda_b200_save); the Python restatement of the layout gives the same bytes
+    from nlp_b200.lda import serialise_model
+    nphi, nz = lda.GetState()
+    assert open(path, "rb").read() == serialise_model(7, (lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus), nphi, nz)
+
+
+def test_model_file_fixture_round_trip(tmp_path):
+    """Load of the committed fixture (tests/golden/lda_model_k3_w9.bin) and Save through the C ABI reproduce it bit for
+    bit; truncated and foreign files are refused"""
+    import io
+    import os
+    raw = open(os.path.join(os.path.dirname(__file__), "golden", "lda_model_k3_w9.bin"), "rb").read()
+    lda = new_lda(5)
+    lda.Load(io.BytesIO(raw))
+    assert (lda.K, lda.w, lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus) == (3, 9, 5.0, 37.0, 1234.0)
+    out = io.BytesIO()
+    lda.Save(out)
+    assert out.getvalue() == raw
+    assert lda.Transform(FIXTURE_A).shape == (3, 9)
+    for bad in (raw[:100], raw[:-1], b"\x00" * len(raw), raw[:32] + b"XXXX" + raw[36:]):
+        with pytest.raises((_lib.LdaB200Error, ValueError), match="EOF|mat.Dense|dimensions"):
+            new_lda(3).Load(io.BytesIO(bad))
 
 
 # ---- bit-exact pieces -------------------------------------------------------------------------------------------
