@@ -389,8 +389,9 @@ def ours(args):
         "kernel_share_of_step": mb_ms.value / dev_ms if dev_ms else None,
         "blend_kernel": {"launches": bl_n.value, "avg_launch_ms": (bl_ms.value / bl_n.value) if bl_n.value else None,
                          "achieved_GBps": (24.0 * K * W * bl_n.value / (bl_ms.value * 1e-3) / 1e9) if bl_ms.value else None},
-        "exchange": {"path": "peer-memory reduce + M-step kernel (CUDA IPC over NVLink)" if peer else
-                     ("ncclAllReduce + blend kernel" if world > 1 else "none (1 GPU)"), "calls": ar_n.value,
+        "exchange": {"path": ("reduce + M-step kernel, reduction and broadcast in the NVSwitch (NVLink multicast, multimem.ld_reduce / "
+                              "multimem.st)" if peer == 2 else "reduce + M-step kernel over unicast peer memory (CUDA IPC over NVLink)")
+                     if peer else ("ncclAllReduce + blend kernel" if world > 1 else "none (1 GPU)"), "calls": ar_n.value,
                      "avg_ms_incl_wait_for_slowest_rank": (ar_ms.value / ar_n.value) if ar_n.value else None,
                      "phases_ms_per_step_rank0": dict(zip(
                          ("opening_barrier_wait_for_slowest_rank", "reduce_blend_over_peer_memory",
@@ -534,7 +535,7 @@ def parity_leg(args, new_lda, rank, world, dev, W, K, md):
             want = o.FitTransform(tuple(sub))
             out[name] = {"sample": "first %d docs, BatchSize=%d, Processes=%d, 2 iterations, seed 0%s" % (
                              n_s, bs, procs, "" if world == 1 else ", %d GPUs, %s" % (
-                                 world, "peer-memory exchange" if path else "ncclAllReduce exchange")),
+                                 world, {2: "NVLink-multicast exchange", 1: "peer-memory exchange", 0: "ncclAllReduce exchange"}[path])),
                          "theta_max_abs_delta": float(np.abs(got - want).max()),
                          "perplexity_rel_delta": float(np.abs(np.array(trace) / o.perplexity_trace - 1).max())}
         if world > 1:

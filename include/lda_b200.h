@@ -290,9 +290,10 @@ int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int
  * the model is unchanged), and both together (mix_ms).  entries = entries replayed.  Best of three launches each. */
 int lda_b200_probe_memory_mix(lda_b200_handle *h, int64_t *entries, float *gather_ms, float *red_ms, float *mix_ms);
 
-/* which multi-GPU step path the last fit used: peer_memory_path = 1 when the reduction of nPhiHat and the M-step run
- * as one kernel over NVLink peer memory (CUDA IPC), 0 when ncclAllReduce + blend is used (fallback, or
- * LDA_B200_PEER_MEMORY=0) */
+/* which multi-GPU step path the last fit used: peer_memory_path = 2 when the reduction of nPhiHat and the M-step run as
+ * one kernel whose reduction and broadcast happen in the NVSwitch (NVLink multicast: multimem.ld_reduce / multimem.st),
+ * 1 when that kernel uses unicast peer loads / stores over CUDA IPC mappings (no multicast support, deterministic mode,
+ * or LDA_B200_NVLS=0), 0 when ncclAllReduce + blend is used (fallback, or LDA_B200_PEER_MEMORY=0) */
 int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks, int32_t *peer_memory_path);
 /* same for the per-step all-reduce (multi-GPU); the time includes waiting for the slowest rank's kernel */
 int lda_b200_last_allreduce_time(const lda_b200_handle *h, float *allreduce_ms, int32_t *allreduce_calls);

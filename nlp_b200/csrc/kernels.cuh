@@ -647,6 +647,9 @@ struct FusedArgs {
     int Kp;
     float A, C;
     double *partials;        // [gridDim.x][Kp] per-block column sums of this rank's slice (summed in block order afterwards)
+    // NVLink multicast variant: the multicast views of this step's nPhiHat buffer and of nPhi (all ranks' copies)
+    const float *mc_hat;
+    float *mc_nphi;
 };
 
 // U rows per thread and iteration: with few ranks a thread has few peer loads of its own, and U independent rows keep
@@ -701,6 +704,89 @@ __global__ void __launch_bounds__(256) peer_reduce_blend_kernel(const FusedArgs 
                 acc.y += sum.y;
                 acc.z += sum.z;
                 acc.w += sum.w;
+            }
+        }
+    }
+    // zero the buffer the next step accumulates into (its readers finished at the previous step's closing barrier)
+    {
+        float4 *z = reinterpret_cast<float4 *>(a.pt.hat[a.cur ^ 1][me]);
+        const int64_t n4 = a.W * VPR;
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x)
+            z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    sm4[threadIdx.x] = acc;
+    __syncthreads();
+    if (rslot == 0) {
+        double sx = 0, sy = 0, sz = 0, sw = 0;
+        for (int s = 0; s < RPB; ++s) {
+            const float4 t = sm4[s * VPR + col];
+            sx += t.x;
+            sy += t.y;
+            sz += t.z;
+            sw += t.w;
+        }
+        double *p = a.partials + (size_t)blockIdx.x * a.Kp + 4 * col;
+        p[0] = sx;
+        p[1] = sy;
+        p[2] = sz;
+        p[3] = sw;
+    }
+}
+
+// The same step with the reduction and the broadcast done by the NVSwitch (NVLS): one multimem.ld_reduce returns the sum
+// of all ranks' nPhiHat for a 16-byte slice (the switch fetches it from every GPU and adds), one multimem.st writes the
+// blended value into every rank's nPhi replica.  Per GPU and direction NVLink carries (R-1)/R * W*K*4 bytes for the
+// reduction plus 1/R of that for the result, against 2 (R-1)/R * W*K*4 for the peer loads / stores above.
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float *mc_addr) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(mc_addr)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float *mc_addr, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) nvls_reduce_blend_kernel(const FusedArgs a) {
+    extern __shared__ float4 sm4[];
+    const int me = a.pt.rank;
+    const int VPR = a.Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    const int64_t stride = (int64_t)gridDim.x * RPB;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 *nphi_local = reinterpret_cast<const float4 *>(a.pt.nphi[me]);
+    for (int64_t r0 = a.row0 + (int64_t)blockIdx.x * RPB + rslot; r0 < a.row1; r0 += stride * U) {
+        float4 sum[U], p[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            if (r < a.row1) {
+                const int64_t e = r * VPR + col;  // float4 index
+                sum[u] = multimem_ld_reduce_add(a.mc_hat + 4 * e);  // U reductions in flight per thread
+                p[u] = nphi_local[e];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t r = r0 + u * stride;
+            if (r < a.row1) {
+                const int64_t e = r * VPR + col;
+                float4 v = p[u];
+                v.x = fmaf(a.A, v.x, a.C * sum[u].x);
+                v.y = fmaf(a.A, v.y, a.C * sum[u].y);
+                v.z = fmaf(a.A, v.z, a.C * sum[u].z);
+                v.w = fmaf(a.A, v.w, a.C * sum[u].w);
+                multimem_st(a.mc_nphi + 4 * e, v);
+                acc.x += sum[u].x;
+                acc.y += sum[u].y;
+                acc.z += sum[u].z;
+                acc.w += sum[u].w;
             }
         }
     }

@@ -26,6 +26,7 @@
 #include "index_internal.h"
 #include "kernels.cuh"
 #include "nccl_dl.h"
+#include "nvls.h"
 #include "pcg.cuh"
 
 using namespace ldab;
@@ -165,6 +166,14 @@ struct lda_b200_handle {
     unsigned epoch = 0;
     int hat_cur = 0;
     std::string peer_note;
+    // NVLink multicast (NVLS): the two nPhiHat buffers and nPhi live in one multicast-backed region per GPU; the step's
+    // exchange kernel reads sums with multimem.ld_reduce and writes every replica with multimem.st (nvls.h)
+    NvlsRegion nvls;
+    bool nvls_wanted = true;
+    bool peer_setup_det = false;  // `deterministic` at the time of peer_setup (NVLS is not used in deterministic mode)
+    float *mc_hat[2] = {nullptr, nullptr};
+    float *mc_nphi = nullptr;
+    std::string nvls_note;
 
     // stats
     int64_t launches = 0;
@@ -481,23 +490,206 @@ void peer_teardown(lda_b200_handle *h) {
     for (void *p : h->ipc_opened) cudaIpcCloseMemHandle(p);
     h->ipc_opened.clear();
     if (h->peer_ok || h->hat_buf[0]) {
-        // the model buffers were plain cudaMalloc allocations shared with the peers
+        // the model buffers were plain cudaMalloc allocations shared with the peers, or slices of the multicast region
+        const bool region = h->nvls.uc_va != 0;
+        if (region && h->stream) cudaStreamSynchronize(h->stream);
         if (h->nphi_ipc) {
-            cudaFree(h->nphi_ipc);
+            if (!region) cudaFree(h->nphi_ipc);
             if (h->nphi == h->nphi_ipc) h->nphi = nullptr;
             h->nphi_ipc = nullptr;
         }
         for (int i = 0; i < 2; ++i) {
-            if (h->hat_buf[i]) cudaFree(h->hat_buf[i]);
+            if (h->hat_buf[i] && !region) cudaFree(h->hat_buf[i]);
             if (h->nphi_hat == h->hat_buf[i]) h->nphi_hat = nullptr;
             h->hat_buf[i] = nullptr;
         }
+        nvls_release(h->nvls);
+        h->mc_hat[0] = h->mc_hat[1] = h->mc_nphi = nullptr;
         if (h->peer_flags) cudaFree(h->peer_flags);
         if (h->peer_nzpart) cudaFree(h->peer_nzpart);
         h->peer_flags = nullptr;
         h->peer_nzpart = nullptr;
     }
     h->peer_ok = false;
+}
+
+// every rank contributes `bytes` bytes; all[q*bytes ..] = rank q's record (ncclAllGather through a device buffer)
+int gather_records(lda_b200_handle *h, const void *mine, size_t bytes, std::vector<char> &all) {
+    const int R = h->nranks;
+    char *d = nullptr;
+    TRY(dalloc(h, &d, bytes * (size_t)R));
+    CU(cudaMemcpyAsync(d + bytes * (size_t)h->rank, mine, bytes, cudaMemcpyHostToDevice, h->stream));
+    NC(nccl().AllGather(d + bytes * (size_t)h->rank, d, bytes, ncclChar, h->comm, h->stream));
+    all.resize(bytes * (size_t)R);
+    CU(cudaMemcpyAsync(all.data(), d, all.size(), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    dfree(h, &d);
+    return 0;
+}
+
+// One multicast object over all ranks' GPUs with `buf_bytes` x 3 (two nPhiHat buffers, nPhi) bound on every GPU.
+// Collective: every rank runs every stage, and after each stage the ranks agree whether all of them succeeded, so that a
+// single failure switches everybody to the unicast peer-memory path (h->nvls.active stays false; nvls_note says why).
+int nvls_setup(lda_b200_handle *h, size_t buf_bytes) {
+    const int R = h->nranks;
+    NvlsRegion &g = h->nvls;
+    nvls_release(g);
+    h->nvls_note.clear();
+    DriverApi &d = drv();
+    struct Rec {
+        int ok, pid;
+        uint64_t token;
+    };
+    auto note = [&](const std::string &s) {
+        if (h->nvls_note.empty()) h->nvls_note = s;
+    };
+    auto agree = [&](bool ok, Rec *first, bool *all_ok) -> int {
+        Rec mine = {ok ? 1 : 0, (int)getpid(), 0};
+        if (h->rank == 0) mine.token = ((uint64_t)getpid() << 32) ^ (uint64_t)time(nullptr) ^ ((uint64_t)(uintptr_t)h >> 4);
+        std::vector<char> all;
+        TRY(gather_records(h, &mine, sizeof mine, all));
+        *all_ok = true;
+        const Rec *r = (const Rec *)all.data();
+        for (int q = 0; q < R; ++q) {
+            if (!r[q].ok) *all_ok = false;
+            for (int p = 0; p < q; ++p)
+                if (r[p].pid == r[q].pid) *all_ok = false;  // ranks of one process would need no file descriptors: not handled here
+        }
+        if (first) *first = r[0];
+        return 0;
+    };
+    bool ok = h->nvls_wanted && !h->deterministic && R >= 2;
+    if (!ok) note(h->deterministic ? "deterministic mode keeps the fixed-order unicast reduction" : "disabled");
+    if (ok && !d.load()) {
+        ok = false;
+        note(d.error);
+    }
+    CUdevice dev = 0;
+    if (ok) {
+        int sup = 0;
+        ok = d.DeviceGet(&dev, h->device) == CUDA_SUCCESS &&
+             d.DeviceGetAttribute(&sup, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) == CUDA_SUCCESS && sup;
+        if (!ok) note("the device does not support multicast objects");
+    }
+    Rec r0;
+    bool all_ok = false;
+    TRY(agree(ok, &r0, &all_ok));
+    if (!all_ok) {
+        note("not every rank can use multicast objects (or ranks share a process)");
+        return 0;
+    }
+    const uint64_t token = r0.token;
+    // sizes: three buffers, each on a 2 MB boundary, the whole rounded to the multicast granularity
+    const size_t slot = (buf_bytes + ((size_t)2 << 20) - 1) & ~(((size_t)2 << 20) - 1);
+    CUmulticastObjectProp mp;
+    memset(&mp, 0, sizeof mp);
+    mp.numDevices = (unsigned)R;
+    mp.size = 3 * slot;
+    mp.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    CUresult cr = d.MulticastGetGranularity(&gran, &mp, CU_MULTICAST_GRANULARITY_RECOMMENDED);
+    ok = cr == CUDA_SUCCESS && gran > 0;
+    if (!ok) note("cuMulticastGetGranularity: " + d.str(cr));
+    if (ok) {
+        mp.size = (mp.size + gran - 1) / gran * gran;
+        g.size = mp.size;
+        g.device = h->device;
+    }
+    // stage 1: rank 0 creates the object and exports it; the others open their sockets
+    int fd = -1, lsock = -1;
+    if (ok && h->rank == 0) {
+        cr = d.MulticastCreate(&g.mc, &mp);
+        ok = cr == CUDA_SUCCESS;
+        if (!ok) note("cuMulticastCreate: " + d.str(cr));
+        if (ok) {
+            cr = d.MemExportToShareableHandle(&fd, g.mc, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+            ok = cr == CUDA_SUCCESS && fd >= 0;
+            if (!ok) note("cuMemExportToShareableHandle: " + d.str(cr));
+        }
+    } else if (ok) {
+        lsock = nvls_listen(token, h->rank);
+        ok = lsock >= 0;
+        if (!ok) note(std::string("unix socket: ") + strerror(errno));
+    }
+    TRY(agree(ok, nullptr, &all_ok));
+    // stage 2: the descriptor travels to every other rank
+    if (all_ok) {
+        if (h->rank == 0) {
+            for (int q = 1; q < R; ++q)
+                if (!nvls_send_fd(token, q, fd)) {
+                    ok = false;
+                    note("could not send the multicast descriptor to rank " + std::to_string(q));
+                }
+        } else {
+            fd = nvls_recv_fd(lsock);
+            ok = fd >= 0;
+            if (!ok) note("did not receive the multicast descriptor");
+            if (ok) {
+                cr = d.MemImportFromShareableHandle(&g.mc, (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+                ok = cr == CUDA_SUCCESS;
+                if (!ok) note("cuMemImportFromShareableHandle: " + d.str(cr));
+            }
+        }
+    }
+    if (fd >= 0) close(fd);
+    if (lsock >= 0) close(lsock);
+    if (all_ok) TRY(agree(ok, nullptr, &all_ok));
+    // stage 3: every device joins the team (all must have joined before anybody binds memory)
+    if (all_ok) {
+        cr = d.MulticastAddDevice(g.mc, dev);
+        ok = cr == CUDA_SUCCESS;
+        if (!ok) note("cuMulticastAddDevice: " + d.str(cr));
+        TRY(agree(ok, nullptr, &all_ok));
+    }
+    // stage 4: physical memory, bound to the object, mapped twice (own memory; multicast view)
+    if (all_ok) {
+        CUmemAllocationProp ap;
+        memset(&ap, 0, sizeof ap);
+        ap.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+        ap.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+        ap.location.id = h->device;
+        ap.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+        CUmemAccessDesc ad;
+        memset(&ad, 0, sizeof ad);
+        ad.location = ap.location;
+        ad.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+        auto step = [&](CUresult r, const char *what) {
+            if (ok && r != CUDA_SUCCESS) {
+                ok = false;
+                note(std::string(what) + ": " + d.str(r));
+            }
+            return ok;
+        };
+        if (step(d.MemCreate(&g.phys, g.size, &ap, 0), "cuMemCreate") &&
+            step(d.MulticastBindMem(g.mc, 0, g.phys, 0, g.size, 0), "cuMulticastBindMem")) {
+            g.bound = true;
+            if (step(d.MemAddressReserve(&g.uc_va, g.size, gran, 0, 0), "cuMemAddressReserve") &&
+                step(d.MemMap(g.uc_va, g.size, 0, g.phys, 0), "cuMemMap")) {
+                g.uc_mapped = true;
+                step(d.MemSetAccess(g.uc_va, g.size, &ad, 1), "cuMemSetAccess");
+            }
+            if (ok && step(d.MemAddressReserve(&g.mc_va, g.size, gran, 0, 0), "cuMemAddressReserve (multicast)") &&
+                step(d.MemMap(g.mc_va, g.size, 0, g.mc, 0), "cuMemMap (multicast)")) {
+                g.mc_mapped = true;
+                step(d.MemSetAccess(g.mc_va, g.size, &ad, 1), "cuMemSetAccess (multicast)");
+            }
+        }
+        TRY(agree(ok, nullptr, &all_ok));
+    }
+    if (!all_ok) {
+        note("a rank failed to set up the multicast region");
+        nvls_release(g);
+        return 0;
+    }
+    g.active = true;
+    char *uc = (char *)(uintptr_t)g.uc_va, *mc = (char *)(uintptr_t)g.mc_va;
+    for (int i = 0; i < 2; ++i) {
+        h->hat_buf[i] = (float *)(uc + (size_t)i * slot);
+        h->mc_hat[i] = (float *)(mc + (size_t)i * slot);
+    }
+    h->nphi_ipc = (float *)(uc + 2 * slot);
+    h->mc_nphi = (float *)(mc + 2 * slot);
+    return 0;
 }
 
 // Allocates the shared model buffers with cudaMalloc, exchanges their CUDA IPC handles with every rank through an
@@ -522,18 +714,28 @@ int peer_setup(lda_b200_handle *h) {
     memset(&mine, 0, sizeof mine);
     mine.pid = (int)getpid();
     mine.dev = h->device;
-    bool ok = soft(cudaMalloc((void **)&h->hat_buf[0], n * sizeof(float)), "cudaMalloc") &&
-              soft(cudaMalloc((void **)&h->hat_buf[1], n * sizeof(float)), "cudaMalloc") &&
-              soft(cudaMalloc((void **)&h->nphi_ipc, n * sizeof(float)), "cudaMalloc") &&
-              soft(cudaMalloc((void **)&h->peer_flags, MAX_PEERS * sizeof(unsigned)), "cudaMalloc") &&
-              soft(cudaMalloc((void **)&h->peer_nzpart, (size_t)MAX_PEERS * h->Kp * sizeof(double)), "cudaMalloc");
+    // The three large buffers come from a multicast-backed region when NVLink multicast is available on every rank
+    // (reduction and broadcast then happen in the switch, and no rank maps another rank's copy); otherwise they are
+    // cudaMalloc allocations whose CUDA IPC handles the ranks exchange.  The small flag / partial-sum arrays are always
+    // shared through IPC.
+    h->peer_setup_det = h->deterministic;
+    TRY(nvls_setup(h, n * sizeof(float)));
+    const bool nvls = h->nvls.active;
+    const int first_ipc = nvls ? 3 : 0;
+    bool ok = true;
+    if (!nvls)
+        ok = soft(cudaMalloc((void **)&h->hat_buf[0], n * sizeof(float)), "cudaMalloc") &&
+             soft(cudaMalloc((void **)&h->hat_buf[1], n * sizeof(float)), "cudaMalloc") &&
+             soft(cudaMalloc((void **)&h->nphi_ipc, n * sizeof(float)), "cudaMalloc");
+    ok = ok && soft(cudaMalloc((void **)&h->peer_flags, MAX_PEERS * sizeof(unsigned)), "cudaMalloc") &&
+         soft(cudaMalloc((void **)&h->peer_nzpart, (size_t)MAX_PEERS * h->Kp * sizeof(double)), "cudaMalloc");
     void *bufs[5] = {h->hat_buf[0], h->hat_buf[1], h->nphi_ipc, h->peer_flags, h->peer_nzpart};
     if (ok) {
         CU(cudaMemsetAsync(h->hat_buf[0], 0, n * sizeof(float), h->stream));
         CU(cudaMemsetAsync(h->hat_buf[1], 0, n * sizeof(float), h->stream));
         CU(cudaMemsetAsync(h->peer_flags, 0, MAX_PEERS * sizeof(unsigned), h->stream));
         CU(cudaMemsetAsync(h->peer_nzpart, 0, (size_t)MAX_PEERS * h->Kp * sizeof(double), h->stream));
-        for (int i = 0; i < 5 && ok; ++i) {
+        for (int i = first_ipc; i < 5 && ok; ++i) {
             mine.ptr[i] = bufs[i];
             ok = soft(cudaIpcGetMemHandle(&mine.mh[i], bufs[i]), "cudaIpcGetMemHandle");
         }
@@ -555,8 +757,8 @@ int peer_setup(lda_b200_handle *h) {
     t.rank = h->rank;
     t.nranks = R;
     for (int q = 0; q < R && ok; ++q) {
-        void *p[5];
-        for (int i = 0; i < 5 && ok; ++i) {
+        void *p[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+        for (int i = first_ipc; i < 5 && ok; ++i) {
             if (q == h->rank) {
                 p[i] = bufs[i];
             } else if (all[(size_t)q].pid == mine.pid) {
@@ -578,6 +780,11 @@ int peer_setup(lda_b200_handle *h) {
             }
         }
         if (!ok) break;
+        if (nvls && q == h->rank) {
+            p[0] = bufs[0];
+            p[1] = bufs[1];
+            p[2] = bufs[2];
+        }
         t.hat[0][q] = (float *)p[0];
         t.hat[1][q] = (float *)p[1];
         t.nphi[q] = (float *)p[2];
@@ -1622,6 +1829,8 @@ int lda_b200_comm_init(lda_b200_handle *h, int32_t rank, int32_t nranks, const v
     h->nranks = nranks;
     const char *env = getenv("LDA_B200_PEER_MEMORY");  // "0" forces the ncclAllReduce + blend path
     h->peer_wanted = !(env && env[0] == '0');
+    env = getenv("LDA_B200_NVLS");  // "0" keeps the peer-memory kernel on unicast loads / stores (no multicast object)
+    h->nvls_wanted = !(env && env[0] == '0');
     return 0;
 }
 
@@ -1649,7 +1858,8 @@ static int fit_begin_impl(lda_b200_handle *h, int64_t W, int64_t D, const int64_
     if (!warm) h->fitted = false;  // nPhi / nZ are re-drawn below: a fit that fails from here on leaves no model behind
     // init (lda.go:193-206): nPhi/nZ are re-initialised on every fit, no warm start.  The device buffers (and the
     // peer mappings) are kept when the shape is unchanged; every value in them is rewritten below.
-    const bool same_shape = h->nphi && h->W == W && h->K == h->cfg.K && (h->nranks == 1 || h->peer_ok || !h->peer_wanted);
+    const bool same_shape = h->nphi && h->W == W && h->K == h->cfg.K && (h->nranks == 1 || h->peer_ok || !h->peer_wanted) &&
+                            (h->nranks == 1 || h->peer_setup_det == h->deterministic);
     if (warm && !same_shape) {
         // keep the model values while moving them into peer-shared buffers: not needed on one GPU, unsupported here
         return fail(h, LDA_B200_EUNSUPPORTED, "PartialFit across a communicator change is not supported");
@@ -1885,9 +2095,13 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 fa.C = (float)Cd;
                 TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
                 fa.partials = h->partials;
+                fa.mc_hat = h->mc_hat[h->hat_cur];
+                fa.mc_nphi = h->mc_nphi;
                 const int bs = blend_block(h->Kp);
                 TRY(ev_begin(h, 4, &ph));
-                if (R <= 2)
+                if (h->nvls.active)
+                    nvls_reduce_blend_kernel<4><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                else if (R <= 2)
                     peer_reduce_blend_kernel<4, 2><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 else if (R <= 4)
                     peer_reduce_blend_kernel<2, 4><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
@@ -2552,7 +2766,7 @@ int lda_b200_comm_info(const lda_b200_handle *h, int32_t *rank, int32_t *nranks,
     if (!h) return LDA_B200_EINVAL;
     if (rank) *rank = h->rank;
     if (nranks) *nranks = h->nranks;
-    if (peer_memory_path) *peer_memory_path = h->peer_ok ? 1 : 0;
+    if (peer_memory_path) *peer_memory_path = h->peer_ok ? (h->nvls.active ? 2 : 1) : 0;
     return 0;
 }
 

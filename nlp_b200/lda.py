@@ -180,12 +180,13 @@ class LatentDirichletAllocation:
         self._comm_ranks = nranks
 
     def CommInfo(self):
-        """(rank, ranks, peer_memory_path) of the handle's communicator; peer_memory_path is True when the multi-GPU
-        step runs as one reduce + M-step kernel over NVLink peer memory instead of ncclAllReduce + blend"""
+        """(rank, ranks, path) of the handle's communicator; path = 2 when the multi-GPU step runs as one reduce + M-step
+        kernel with the reduction and the broadcast done in the NVSwitch (NVLink multicast), 1 when that kernel uses
+        unicast peer loads / stores, 0 for ncclAllReduce + blend (truthy = one kernel over NVLink)"""
         r, n, p = C.c_int32(0), C.c_int32(1), C.c_int32(0)
         if self._h is not None:
             _lib.lib().lda_b200_comm_info(self._h, C.byref(r), C.byref(n), C.byref(p))
-        return r.value, n.value, bool(p.value)
+        return r.value, n.value, p.value
 
     def ToCSC(self, m):
         """sparse.ToCSC() (lda.go:464-466) of a scipy CSR term x document matrix on the GPU -> nlp_b200.CSC"""

@@ -107,6 +107,11 @@ typedef struct {
      * in index order (lda.go:299-317 G times).  This is the semantics of the G-GPU path; the
      * reference's own Processes > 1 schedule is racy and not reproducible. */
     int64_t SyncGroup;
+    /* HoistPow != 0 (not in the reference): pow((1 - rhoTheta), v) is evaluated once per token instead of 2K times
+     * (lda.go:247-248 call it inside the loop over k).  pow is a pure function of its two arguments, so every result
+     * keeps its bits (tests/test_oracle_golden.py checks that); it only makes the oracle fast enough to check whole
+     * BASELINE configurations.  The CPU baseline legs of bench.py leave it off: they time the reference's loop as is. */
+    int64_t HoistPow;
 } oracle_lda;
 
 /* term x document matrix in CSC: column j = document j, rows = word ids, in stored order.
@@ -193,6 +198,14 @@ static inline void token_update(const oracle_lda *l, int64_t i, int64_t j, doubl
         gammaSum += gamma[k];
     }
     for (int64_t k = 0; k < K; k++) gamma[k] /= gammaSum;
+    if (l->HoistPow) {
+        const double pw = pow((1.0 - rhoTheta), v);
+        for (int64_t k = 0; k < K; k++) {
+            int64_t thetaInd = j * K + k;
+            nTheta[thetaInd] = ((pw * nTheta[thetaInd]) + ((1 - pw) * wc * gamma[k]));
+        }
+        return;
+    }
     for (int64_t k = 0; k < K; k++) {
         /* Eqn. 9 */
         int64_t thetaInd = j * K + k;
@@ -254,8 +267,12 @@ static void estep_mini_batch(oracle_lda *l, mini_batch *mb, const double *wc, do
                 gammaSum += gamma[k];
             }
             for (int64_t k = 0; k < K; k++) gamma[k] /= gammaSum;
+            const double pw = l->HoistPow ? pow((1.0 - rhoTheta), v) : 0.0;
             for (int64_t k = 0; k < K; k++) {
                 int64_t thetaInd = j * K + k;
+                if (l->HoistPow)
+                    nTheta[thetaInd] = ((pw * nTheta[thetaInd]) + ((1 - pw) * wc[j] * gamma[k]));
+                else
                 nTheta[thetaInd] =
                     ((pow((1.0 - rhoTheta), v) * nTheta[thetaInd]) + ((1 - pow((1.0 - rhoTheta), v)) * wc[j] * gamma[k]));
                 /* sufficient stats: note there is no factor v (lda.go:293) */
@@ -574,6 +591,7 @@ FIELD_RW(double, Alpha)
 FIELD_RW(double, Eta)
 FIELD_RW(int64_t, Processes)
 FIELD_RW(int64_t, SyncGroup)
+FIELD_RW(int64_t, HoistPow)
 FIELD_RW(double, rhoPhiT)
 FIELD_RW(double, rhoThetaT)
 FIELD_RW(double, wordsInCorpus)

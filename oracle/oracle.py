@@ -71,7 +71,8 @@ _FIELDS = {
     "Iterations": C.c_int64, "PerplexityTolerance": C.c_double, "PerplexityEvaluationFrequency": C.c_int64,
     "BatchSize": C.c_int64, "K": C.c_int64, "BurnInPasses": C.c_int64, "TransformationPasses": C.c_int64,
     "MeanChangeTolerance": C.c_double, "ChangeEvaluationFrequency": C.c_int64, "Alpha": C.c_double,
-    "Eta": C.c_double, "Processes": C.c_int64, "SyncGroup": C.c_int64, "rhoPhiT": C.c_double, "rhoThetaT": C.c_double,
+    "Eta": C.c_double, "Processes": C.c_int64, "SyncGroup": C.c_int64, "HoistPow": C.c_int64,
+    "rhoPhiT": C.c_double, "rhoThetaT": C.c_double,
     "wordsInCorpus": C.c_double,
 }
 

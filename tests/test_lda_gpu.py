@@ -586,6 +586,49 @@ def test_failed_fit_leaves_no_model():
         lda.Transform(FIXTURE_A)
 
 
+# ---- oracle parity on a BASELINE configuration in full, and at K = 256 over several large minibatches ---------------------
+@pytest.mark.parametrize("b", [100, 2048], ids=["BatchSize100-reference-default", "BatchSize2048"])
+def test_config2_full_parity(b):
+    """BASELINE configs[1] in full -- K = 100, 18,846 documents x 50k words, ~2.5M non-zeros -- for 5 iterations at
+    Processes = 1 against the oracle: per-iteration perplexity within 1e-3 relative, doc-topic matrix within 2e-3
+    (BASELINE.md section 3).  The oracle runs with HoistPow (bit-identical, see oracle/lda_oracle.c) to finish in seconds."""
+    D, W, K, md = corpus_synth.shape("C2")
+    m = synth(D, W, md, block=2048)
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=5, BatchSize=b)
+    o = new_oracle(K, HoistPow=1, **f)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(K, **f)
+    got = lda.FitTransform(m)
+    rel = np.abs(np.array(lda.PerplexityTrace) / o.perplexity_trace - 1).max()
+    print("config2 b=%d: max rel perplexity delta %.3g, max |dtheta| %.3g, perplexity %s" % (
+        b, rel, np.abs(got - want).max(), np.round(o.perplexity_trace, 1)))
+    assert rel <= PERP_RTOL
+    assert np.abs(got - want).max() <= THETA_ATOL
+    np.testing.assert_allclose(lda.GetState()[1], o.get_state()[1], rtol=1e-3)
+    assert (lda.rhoPhiT, lda.rhoThetaT, lda.wordsInCorpus) == (o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus)
+
+
+@pytest.mark.parametrize("procs", [1, 4], ids=["Processes1", "Processes4"])
+def test_k256_large_minibatches_parity(procs):
+    """the K = 256 throughput kernel on 4,500 documents in minibatches of 1,024 (five minibatches, the last one short), one
+    at a time and four per launch, 4 iterations, against the oracle"""
+    m = synth(4500, 20000, 120, block=1024)
+    f = dict(PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0, Iterations=4, BatchSize=1024)
+    o = new_oracle(256, HoistPow=1, SyncGroup=procs, **f)
+    want = o.FitTransform(tuple(m))
+    lda = new_lda(256, Processes=procs, **f)
+    got = lda.FitTransform(m)
+    np.testing.assert_allclose(lda.PerplexityTrace, o.perplexity_trace, rtol=PERP_RTOL)
+    assert np.abs(got - want).max() <= THETA_ATOL
+    np.testing.assert_allclose(lda.GetState()[1], o.get_state()[1], rtol=1e-3)
+    held = synth(1500, 20000, 120, block=1024, seed=777)
+    o.set_state(*lda.GetState())
+    t, passes = lda.Transform(held, return_passes=True)
+    t_want, p_want = o.Transform(tuple(held), return_passes=True)
+    same = passes == p_want
+    assert same.mean() >= 0.95 and np.abs(t - t_want)[:, same].max() <= THETA_ATOL and np.abs(t - t_want).max() <= 0.035
+
+
 # ---- size-independent properties at a BASELINE-sized configuration -----------------------------------------------------
 def test_config2_properties():
     """configs[1] shape (18,846 docs x 50k vocab, K=100): columns sum to 1, perplexity ends up falling, refit reproducible

@@ -32,10 +32,25 @@ def _owned_view(indptr, ind, data, D, b, rank, world):
     return np.concatenate(([0], np.cumsum(lens))), ind[sel], data[sel]
 
 
-def _worker(rank, world, port, case, conc, peer, ret):
+PATHS = {"nvls": 2, "peer-memory": 1, "nccl-allreduce": 0}
+
+
+def _multicast_supported():
+    try:
+        from cuda.bindings import driver as cu
+        cu.cuInit(0)
+        dev = cu.cuDeviceGet(0)[1]
+        return bool(cu.cuDeviceGetAttribute(cu.CUdevice_attribute.CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev)[1])
+    except Exception:
+        return True
+
+
+def _worker(rank, world, port, case, conc, path, ret):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), LOCAL_RANK=str(rank),
-                      LDA_B200_PEER_MEMORY="1" if peer else "0")
+                      LDA_B200_PEER_MEMORY="0" if path == "nccl-allreduce" else "1",
+                      LDA_B200_NVLS="1" if path == "nvls" else "0")
+    want_path = PATHS[path] if (path != "nvls" or _multicast_supported()) else 1
     import torch
     import torch.distributed as dist
     torch.cuda.set_device(rank)
@@ -57,7 +72,7 @@ def _worker(rank, world, port, case, conc, peer, ret):
         lda.BatchSize, lda.Iterations = b, iters
         lda.PerplexityEvaluationFrequency, lda.PerplexityTolerance = 1, 0.0
         theta = lda.FitTransform(m)
-        assert lda.CommInfo() == (rank, world, peer), lda.CommInfo()
+        assert lda.CommInfo() == (rank, world, want_path), lda.CommInfo()
         nphi, nz = lda.GetState()
         held = corpus_synth.generate(3 * b + 7, W, seed=99, block=b, mean_distinct=40, n_topics=16)
         t, passes = lda.Transform(CSC(W, 3 * b + 7, *held), return_passes=True)
@@ -87,11 +102,12 @@ def _ids(c):
     return "R%dxC%d-K%d-D%d" % (c[0], c[1], c[2][2], c[2][0])
 
 
-@pytest.mark.parametrize("peer", [True, False], ids=["peer-memory", "nccl-allreduce"])
+@pytest.mark.parametrize("path", ["nvls", "peer-memory", "nccl-allreduce"])
 @pytest.mark.parametrize("cfg", CASES, ids=_ids)
-def test_multi_gpu_fit_matches_sync_group_oracle(cfg, peer):
-    """peer=True: reduction + M-step fused in one kernel over NVLink peer memory (CUDA IPC); peer=False: the
-    ncclAllReduce + blend fallback.  Both must give the same model as the oracle's SyncGroup = R*C schedule."""
+def test_multi_gpu_fit_matches_sync_group_oracle(cfg, path):
+    """nvls: reduction + M-step fused in one kernel whose sums and broadcasts happen in the NVSwitch (multimem.ld_reduce /
+    multimem.st on a multicast object); peer-memory: the same kernel over unicast peer loads / stores (CUDA IPC);
+    nccl-allreduce: the ncclAllReduce + blend fallback.  All must give the model of the oracle's SyncGroup = R*C schedule."""
     import torch
     import torch.multiprocessing as mp
     R, conc, case = cfg
@@ -101,7 +117,7 @@ def test_multi_gpu_fit_matches_sync_group_oracle(cfg, peer):
     from oracle import oracle as O
     D, W, K, b, iters = case
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(R, _free_port(), case, conc, peer, ret), nprocs=R, join=True)
+    mp.spawn(_worker, args=(R, _free_port(), case, conc, path, ret), nprocs=R, join=True)
     rs = [ret[r] for r in range(R)]
     r0 = rs[0]
 

@@ -145,3 +145,19 @@ def test_committed_golden_vectors_reproduce():
         np.testing.assert_allclose(theta[:, :4], case["theta_first_docs"], rtol=1e-7, atol=1e-12)
         assert [o.rhoPhiT, o.rhoThetaT, o.wordsInCorpus] == case["counters"]
         assert list(o.rnd_state) == case["rnd_state"]
+
+
+def test_hoisted_pow_keeps_every_bit():
+    """HoistPow evaluates pow((1 - rhoTheta), v) once per token instead of 2K times (lda.go:247-248); pow is pure, so
+    FitTransform, the perplexity trace, Transform and the model state are bit-identical -- which is what lets the large
+    parity tests use it"""
+    import corpus_synth
+    D, W, K = 300, 900, 17
+    m = (W, D) + tuple(corpus_synth.generate(D, W, block=64, mean_distinct=30, n_topics=16))
+    outs = []
+    for hoist in (0, 1):
+        o = O.LatentDirichletAllocation(K, seed=0)
+        o.Iterations, o.BatchSize, o.PerplexityEvaluationFrequency, o.PerplexityTolerance, o.HoistPow = 3, 64, 1, 0.0, hoist
+        theta = o.FitTransform(m)
+        outs.append((theta, o.perplexity_trace, o.Transform(m), o.get_state()[0], o.get_state()[1]))
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))

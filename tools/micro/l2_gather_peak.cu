@@ -51,6 +51,15 @@ __global__ void __launch_bounds__(256) red_probe(float *hat, const int *ids, int
         if (RW == 1) {
 #pragma unroll
             for (int j = 0; j < 4 * NV; ++j) atomicAdd(dst + j * 32 + lane, 1.f);
+        } else if (RW == 4) {   // 32-bit integer adds, 4 bytes per lane
+#pragma unroll
+            for (int j = 0; j < 4 * NV; ++j) atomicAdd(reinterpret_cast<unsigned *>(dst) + j * 32 + lane, 1u);
+        } else if (RW == 5) {   // 64-bit integer adds, 8 bytes per lane (the deterministic mode's fixed-point image)
+#pragma unroll
+            for (int j = 0; j < 2 * NV; ++j) atomicAdd(reinterpret_cast<unsigned long long *>(dst) + j * 32 + lane, 1ull);
+        } else if (RW == 6) {   // float64 adds, 8 bytes per lane
+#pragma unroll
+            for (int j = 0; j < 2 * NV; ++j) atomicAdd(reinterpret_cast<double *>(dst) + j * 32 + lane, 1.0);
         } else if (RW == 2) {
 #pragma unroll
             for (int j = 0; j < 2 * NV; ++j) red_add_v2(dst + 2 * (j * 32 + lane), make_float2(1.f, 2.f));
@@ -215,6 +224,12 @@ int main(int argc, char **argv) {
             printf("  %d CTAs/SM  red scalar    : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
             ms = time_ms([&] { red_probe<2, NV><<<grid, 256>>>(hat, ids, n / 2); }, 5);
             printf("  %d CTAs/SM  red v2        : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
+            ms = time_ms([&] { red_probe<4, NV><<<grid, 256>>>(hat, ids, n / 2); }, 5);
+            printf("  %d CTAs/SM  red u32       : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
+            ms = time_ms([&] { red_probe<5, NV><<<grid, 256>>>(hat, ids, n / 2); }, 5);
+            printf("  %d CTAs/SM  red u64       : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
+            ms = time_ms([&] { red_probe<6, NV><<<grid, 256>>>(hat, ids, n / 2); }, 5);
+            printf("  %d CTAs/SM  red f64       : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
             CK(cudaFuncSetAttribute(red_probe<3, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 4 * 128 * NV * 4));
             ms = time_ms([&] { red_probe<3, NV><<<grid, 256, 8 * 4 * 128 * NV * 4>>>(hat, ids, n / 2); }, 5);
             printf("  %d CTAs/SM  TMA bulk red  : %7.3f ms  %7.2f TB/s (reduction payload)\n", occ, ms, gb / 2 / ms);
