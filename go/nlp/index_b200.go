@@ -135,19 +135,22 @@ func (b *B200LinearScanIndex) IndexTransform(lda *LatentDirichletAllocation, m m
 	if err != nil {
 		return err
 	}
-	desc, keep := matrix(m)
+	f := flatten(m)
 	_, c := m.Dims()
 	handles := make([]C.int64_t, c)
 	for j := range handles {
 		handles[j] = C.int64_t(b.next + int64(j))
 	}
+	theta0 := lda.draws(c) // lda.go:422-426 when the caller assigned Rnd, nil otherwise
 	rnd := lda.pcg()
 	var hp *C.int64_t
 	if c > 0 {
 		hp = &handles[0]
 	}
-	rc := C.lda_b200_transform_into_index(h, &desc, nil, &rnd, C.double(lda.rhoThetaT), b.h, hp)
-	runtime.KeepAlive(keep)
+	rc := C.lda_b200_transform_into_index_flat(h, f.format, f.rows, f.cols, ptrI(f.ptr), ptrI(f.ind), ptrF(f.data), ptrF(theta0), &rnd,
+		C.double(lda.rhoThetaT), b.h, hp)
+	runtime.KeepAlive(f)
+	runtime.KeepAlive(theta0)
 	if rc != 0 {
 		return lda.err()
 	}

@@ -55,6 +55,10 @@ int lda_b200_index_add(lda_b200_index *ix, int32_t dim, int64_t n, const double 
  * minibatches (a sharded index: search every rank's index and merge). */
 int lda_b200_transform_into_index(lda_b200_handle *h, const lda_b200_matrix *m, const double *theta0, lda_b200_pcg *rnd,
                                   double rho_theta_t, lda_b200_index *ix, const int64_t *ids);
+/* the same call with the matrix descriptor spread over scalar arguments (the form cgo can call, see lda_b200_fit_flat) */
+int lda_b200_transform_into_index_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                                       const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                                       double rho_theta_t, lda_b200_index *ix, const int64_t *ids);
 
 /* Remove(id), index.go:117-135: drops the first vector indexed under id, keeping the order of the others; unknown ids
  * are ignored. */

@@ -106,6 +106,8 @@ SYMBOLS.update({
     "lda_b200_index_last_error": (C.c_char_p, [_P]),
     "lda_b200_index_add": (C.c_int, [_P, C.c_int32, C.c_int64, _P, C.c_int64, _P]),
     "lda_b200_transform_into_index": (C.c_int, [_P, C.POINTER(Matrix), _P, C.POINTER(Pcg), C.c_double, _P, _P]),
+    "lda_b200_transform_into_index_flat": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P, _P, _P, C.POINTER(Pcg),
+                                                     C.c_double, _P, _P]),
     "lda_b200_index_remove": (C.c_int, [_P, C.c_int64]),
     "lda_b200_index_len": (C.c_int64, [_P]),
     "lda_b200_index_search": (C.c_int, [_P, C.c_int64, _P, C.c_int64, C.c_int32, _P, _P, _P]),

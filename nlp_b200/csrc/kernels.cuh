@@ -479,6 +479,232 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Several documents per warp for mid-sized K (64 < K <= 256): GD documents side by side, each on LANES = 32 / GD lanes,
+// every lane holding NV float4 slices of its document's topic axis.  Same arithmetic, same shared-memory ring of rows of
+// C (one ring per document, filled by cp.async R positions ahead of the document's token stream) as scvb0_docs32_kernel;
+// what changes is the instruction count per token visit: the sum over topics is a log2(LANES)-level butterfly whose
+// SHFL / FADD instructions serve GD documents at once, and so do the per-token broadcasts, the loop control and the
+// address arithmetic.  ncu on the Transform kernel (profiles/r02/ncu_c3_c4_c5.txt) showed 69 warp instructions per
+// visit at 81 % issue utilisation with only 25 of them the FFMAs of the update, i.e. an issue-bound kernel whose
+// overhead instructions this layout amortises.
+// The documents of a warp walk their passes in lock step (a pass lasts as long as the warp's longest document; the
+// launch order is longest-first, so neighbours differ by a token or two); a document whose burn-in has converged
+// (lda.go:251-259) idles until the others are done.  Rows are consumed in the order they were requested, per document,
+// so a lane's cp.async groups are exactly its document's token stream and wait_group<R-1> is the row of the current token.
+constexpr int docsg_ring_rows(int GD, int NV) { return GD * NV <= 8 ? 4 : 3; }
+constexpr int docsg_min_blocks(int GD, int NV) { return NV <= 4 ? 3 : 2; }
+constexpr int docsg_smem_bytes(int GD, int NV) { return 8 * GD * docsg_ring_rows(GD, NV) * NV * (32 / GD) * 16; }
+
+template <int GD, int NV, bool FULLK, bool FIT, bool DET = false>
+__global__ void __launch_bounds__(256, docsg_min_blocks(GD, NV)) scvb0_docsg_kernel(const DocsArgs a, const int *__restrict__ order) {
+    constexpr int LANES = 32 / GD;
+    constexpr int R = docsg_ring_rows(GD, NV);
+    extern __shared__ float4 ring_all[];
+    const int lane = threadIdx.x & 31;
+    const int g = lane % LANES;
+    const int grp = lane / LANES;
+    // slot s, slice v of this lane's document: ring[(s*NV+v)*LANES]
+    float4 *ring = ring_all + (threadIdx.x >> 5) * (GD * R * NV * LANES) + grp * (R * NV * LANES) + g;
+    const int Kp = FULLK ? 4 * LANES * NV : a.Kp;
+    const unsigned row_vecs = (unsigned)Kp >> 2;
+    unsigned lane_vec = (unsigned)g;
+    asm volatile("" : "+r"(lane_vec));
+    const float alpha = a.alpha;
+    const char *__restrict__ cmat_b = reinterpret_cast<const char *>(a.cmat);
+    const float *__restrict__ tab = a.log1m_rho;
+    const int passes = a.passes;
+    const int total_passes = passes + (FIT ? 1 : 0);
+
+    bool ok[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) ok[v] = FULLK || 4 * (v * LANES + g) < Kp;
+    auto issue = [&](int slot, int w) {  // this lane's slices of row w into ring slot `slot`; closes one cp.async group
+        if (w >= 0) {
+            const char *src = cmat_b + (size_t)((unsigned)w * row_vecs + lane_vec) * 16u;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v]) cp_async16(ring + (slot * NV + v) * LANES, reinterpret_cast<const float *>(src + 16 * LANES * v));
+        }
+        cp_async_commit();
+    };
+
+    for (;;) {
+        int d0 = 0;
+        if (lane == 0) d0 = atomicAdd(a.doc_counter, GD);
+        d0 = __shfl_sync(FULL, d0, 0);
+        if (a.doc_begin + d0 >= a.doc_end) break;
+        const int pos = a.doc_begin + d0 + grp;
+        const bool valid = pos < a.doc_end;
+        const int doc = valid ? (order ? order[pos] : pos) : 0;
+        int len = 0;
+        const int32_t *dind = a.ind;
+        const float *dval = a.val;
+        float wcj = 0.f, hat_scale = 0.f;
+        if (valid) {
+            const int64_t base = a.doc_ptr[doc];
+            len = (int)(a.doc_ptr[doc + 1] - base);
+            dind += base;
+            dval += base;
+            wcj = a.wc[doc];
+            if (FIT) hat_scale = a.hat_scale[(doc - a.mb_origin) / a.mb_docs];
+        }
+        const int stored = len;
+        if (total_passes == 0) len = 0;
+        int maxlen = len;
+#pragma unroll
+        for (int o = 16; o >= LANES; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+        if (maxlen == 0) {  // no tokens: the nTheta rows keep their values
+            if (valid && a.passes_out && g == 0) a.passes_out[doc] = stored > 0 ? 0 : -1;
+            continue;
+        }
+        const bool live = len > 0;  // this group has a document with tokens
+        float *trow = a.theta + (int64_t)doc * Kp + 4 * g;
+        float4 tha[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const float4 t = (live && ok[v]) ? *reinterpret_cast<const float4 *>(trow + 4 * LANES * v) : make_float4(0.f, 0.f, 0.f, 0.f);
+            tha[v] = make_float4(t.x + alpha, t.y + alpha, t.z + alpha, t.w + alpha);
+        }
+        // word id `idx` positions into the token stream that starts at pass pi (-1 past the end of the last pass)
+        auto stream_word = [&](int pi, int idx) -> int {
+            if (idx >= len) {
+                pi += idx / len;
+                idx %= len;
+            }
+            return pi < total_passes ? dind[idx] : -1;
+        };
+        auto theta_sum = [&]() -> double {  // sum_k nTheta[j,k]  (lda.go:226-229, 252-255), per document
+            double s = 0.0;
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v]) s += ((double)(tha[v].x - alpha) + (tha[v].y - alpha)) + ((double)(tha[v].z - alpha) + (tha[v].w - alpha));
+            return group_sum_d<LANES>(s);
+        };
+        int slot = 0;
+        auto prime = [&](int first_pass) {  // the rows of the first R stream positions from (first_pass, 0)
+            if (live)
+                for (int s = 0; s < R; ++s) issue(s, stream_word(first_pass, s));
+            slot = 0;
+        };
+        prime(0);
+
+        bool done = !live;  // burn-in of this document is over (converged, or there is no document)
+        int executed = 0;
+        double prev = 0.0;
+        int pi = 0;
+        while (pi < total_passes) {
+            const bool burn = pi < passes;
+            if (burn && __all_sync(FULL, done)) {  // every document of the warp has converged early
+                if (!FIT) break;
+                pi = passes;
+                continue;
+            }
+            const bool idle = !live || (burn && done);
+            const int counter = pi + 1;
+            const bool chk = burn && a.change_freq > 0 && counter % a.change_freq == 0;
+            if (chk && 1 < passes) {  // lda.go:224-230
+                const double s0 = theta_sum();
+                if (!idle) prev = s0;
+            }
+            const float l1m = tab[min(counter, passes)];  // lda.go:231 / :274
+            auto run_pass = [&](auto is_main) {
+                constexpr bool MAINP = decltype(is_main)::value;
+                for (int tile = 0; tile < maxlen; tile += LANES) {
+                    const int my = tile + g;
+                    const bool has = !idle && my < len;
+                    const int wi = has ? dind[my] : 0;
+                    const float q = has ? -expm1f(dval[my] * l1m) : 0.f;
+                    const int la = has ? stream_word(pi, my + R) : -1;
+                    const int ntile = min(LANES, maxlen - tile);
+                    for (int t = 0; t < ntile; ++t) {
+                        const float qt = __shfl_sync(FULL, q, t, LANES);
+                        const int wn = __shfl_sync(FULL, la, t, LANES);
+                        const int w = MAINP ? __shfl_sync(FULL, wi, t, LANES) : 0;
+                        const bool act = !idle && tile + t < len;  // uniform inside a document's lanes
+                        float4 c[NV];
+                        if (act) {
+                            cp_async_wait<R - 1>();  // the oldest outstanding group (this token's row) has landed
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) c[v] = ok[v] ? ring[(slot * NV + v) * LANES] : make_float4(0.f, 0.f, 0.f, 0.f);
+                            issue(slot, wn);  // refill the slot just consumed with the row R positions ahead
+                            slot = slot + 1 == R ? 0 : slot + 1;
+                        } else {
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) c[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                        float p0 = 0.f, p1 = 0.f;
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            p0 = fmaf(c[v].x, tha[v].x, p0);
+                            p1 = fmaf(c[v].y, tha[v].y, p1);
+                            p0 = fmaf(c[v].z, tha[v].z, p0);
+                            p1 = fmaf(c[v].w, tha[v].w, p1);
+                        }
+                        const float sum = group_sum<LANES>(p0 + p1);
+                        if (act) {
+                            const float r = fast_rcp(sum);
+                            const float keep = 1.0f - qt;
+                            const float mix = qt * wcj * r;
+                            const float aq = alpha * qt;
+                            if (MAINP) {
+                                const float sc = hat_scale * r;
+                                const size_t hoff = (size_t)((unsigned)w * row_vecs + lane_vec) * 4u;  // in elements
+#pragma unroll
+                                for (int v = 0; v < NV; ++v)
+                                    if (ok[v]) {
+                                        const float4 add = make_float4(sc * c[v].x * tha[v].x, sc * c[v].y * tha[v].y,
+                                                                       sc * c[v].z * tha[v].z, sc * c[v].w * tha[v].w);
+                                        if (DET)
+                                            red_add_fx4(a.hat_fx + hoff + 4 * LANES * v, add, a.fx_scale);
+                                        else
+                                            red_add_v4(a.nphi_hat + hoff + 4 * LANES * v, add);
+                                    }
+                            }
+#pragma unroll
+                            for (int v = 0; v < NV; ++v) {
+                                tha[v].x = fmaf(tha[v].x, fmaf(mix, c[v].x, keep), aq);
+                                tha[v].y = fmaf(tha[v].y, fmaf(mix, c[v].y, keep), aq);
+                                tha[v].z = fmaf(tha[v].z, fmaf(mix, c[v].z, keep), aq);
+                                tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
+                            }
+                        }
+                    }
+                }
+            };
+            if (FIT && !burn)
+                run_pass(std::true_type{});
+            else
+                run_pass(std::false_type{});
+            if (burn && !idle) executed = counter;
+            if (chk && counter < passes) {  // lda.go:251-259
+                const double sm = theta_sum();
+                if (!idle && fabs(sm - prev) / (double)a.K < (double)a.change_tol) {
+                    done = true;
+                    cp_async_wait<0>();  // rows requested for the passes that will not run
+                    if (FIT) {           // burn-in converged early: the sufficient-statistics pass comes next (lda.go:274)
+                        for (int s = 0; s < R; ++s) issue(s, stream_word(passes, s));
+                        slot = 0;
+                    }
+                }
+            }
+            ++pi;
+        }
+        if (live) {
+            cp_async_wait<0>();
+#pragma unroll
+            for (int v = 0; v < NV; ++v)
+                if (ok[v])
+                    *reinterpret_cast<float4 *>(trow + 4 * LANES * v) =
+                        make_float4(fmaxf(tha[v].x - alpha, 0.f), fmaxf(tha[v].y - alpha, 0.f), fmaxf(tha[v].z - alpha, 0.f),
+                                    fmaxf(tha[v].w - alpha, 0.f));
+            if (a.passes_out && g == 0) a.passes_out[doc] = executed;
+        } else if (valid && a.passes_out && g == 0) {
+            a.passes_out[doc] = stored > 0 ? 0 : -1;
+        }
+    }
+}
+
 // ln(1 - S/(Tau + t0 + c)^Kappa), c = 0..n-1  (LearningSchedule.Calc, lda.go:30-32), evaluated in float64
 __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, int n, float *out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;

@@ -123,6 +123,9 @@ struct lda_b200_handle {
     double *partials = nullptr;  // per-block partial sums of the cross-block reductions (summed in block order)
     size_t partials_cap = 0;
     bool deterministic = false;  // sufficient statistics accumulated in 64-bit fixed point (lda_b200_set_deterministic)
+    // documents per warp of the 64 < K <= 256 kernels: 1 = scvb0_docs32_kernel, 2 / 4 = scvb0_docsg_kernel
+    // (LDA_B200_DOCS_PER_WARP_FIT / LDA_B200_DOCS_PER_WARP_TRANSFORM override the defaults)
+    int docs_per_warp_fit = 1, docs_per_warp_transform = 1;
     unsigned long long *hat_fx = nullptr;
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -350,9 +353,39 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
         KCHECK();
         return 0;
     };
+    // 64 < K <= 256: GD documents per warp (scvb0_docsg_kernel), longest first
+    auto grouped = [&](auto kern, int gd, int nv) -> int {
+        const int smem = docsg_smem_bytes(gd, nv);
+        CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int occ = 1;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        if (occ < 1) occ = 1;
+        const int64_t warps = ((int64_t)n_docs + gd - 1) / gd;
+        const int grid = (int)std::min<int64_t>((warps + 7) / 8, (int64_t)h->sms * occ);
+        kern<<<grid, 256, smem, st>>>(a, order);
+        KCHECK();
+        return 0;
+    };
     // deterministic mode (fit only): the variants that accumulate the sufficient statistics in fixed point
     constexpr bool CAN_DET = FIT;
     const bool det = CAN_DET && a.hat_fx != nullptr;
+    const int gd = det ? 1 : (FIT ? h->docs_per_warp_fit : h->docs_per_warp_transform);
+    if (gd > 1 && vecs > 16 && vecs <= 64) {
+        const bool full = vecs == 32 || vecs == 64;
+        const bool wide_k = vecs > 32;  // 128 < K <= 256
+#define LDA_GROUPED(GD, NV)                                                                 \
+    do {                                                                                    \
+        if (full) return grouped(scvb0_docsg_kernel<GD, NV, true, FIT, false>, GD, NV);     \
+        return grouped(scvb0_docsg_kernel<GD, NV, false, FIT, false>, GD, NV);              \
+    } while (0)
+        if (gd == 2) {
+            if (wide_k) LDA_GROUPED(2, 4);
+            LDA_GROUPED(2, 2);
+        }
+        if (wide_k) LDA_GROUPED(4, 8);
+        LDA_GROUPED(4, 4);
+#undef LDA_GROUPED
+    }
 #define LDA_NARROW(L)                                                              \
     do {                                                                           \
         if (det) return narrow(scvb0_docs_kernel<L, 1, 4, FIT, CAN_DET>, L);       \
@@ -1708,6 +1741,13 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         TRY(dalloc(h, &h->err_flag, 1));
         TRY(dalloc(h, &h->dacc, 2));
         CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
+        auto env_gd = [](const char *name, int dflt) {
+            const char *e = getenv(name);
+            const int v = e ? atoi(e) : dflt;
+            return (v == 1 || v == 2 || v == 4) ? v : dflt;
+        };
+        h->docs_per_warp_fit = env_gd("LDA_B200_DOCS_PER_WARP_FIT", h->docs_per_warp_fit);
+        h->docs_per_warp_transform = env_gd("LDA_B200_DOCS_PER_WARP_TRANSFORM", h->docs_per_warp_transform);
         h->stage_bytes = (size_t)256 << 20;
         CU(cudaMalloc(&h->stage, h->stage_bytes));
         CU(cudaMallocHost((void **)&h->h_pinned, 64));
@@ -2485,6 +2525,13 @@ int lda_b200_perplexity_flat(lda_b200_handle *h, int32_t format, int64_t rows, i
                              double rho_theta_t, double *out) {
     const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
     return lda_b200_perplexity_matrix(h, &m, theta0, rnd, rho_theta_t, out);
+}
+
+int lda_b200_transform_into_index_flat(lda_b200_handle *h, int32_t format, int64_t rows, int64_t cols, const int64_t *ptr,
+                                       const int64_t *ind, const double *data, const double *theta0, lda_b200_pcg *rnd,
+                                       double rho_theta_t, lda_b200_index *ix, const int64_t *ids) {
+    const lda_b200_matrix m = flat_matrix(format, rows, cols, ptr, ind, data);
+    return lda_b200_transform_into_index(h, &m, theta0, rnd, rho_theta_t, ix, ids);
 }
 
 // ---- Save / Load (layout in include/lda_b200.h) ---------------------------------------------------------------------
