@@ -11,6 +11,8 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <memory>
 #include <string>
 #include <thread>
 #include <utility>
@@ -40,6 +42,20 @@ struct Segment {
     int64_t l0;      // first local row
 };
 
+// Word ids of a pageable caller array on their way to the device behind the first iteration's launches: the copies into
+// the page-locked staging ring are host work (memcpy), so they run on their own thread while the calling thread queues the
+// launches.  recorded = number of sub-ranges whose "ids in place" event has been recorded on the copy stream; a launch may
+// only be made to wait on an event that has been recorded (waiting on an unrecorded event is a no-op in CUDA).
+struct UploadJob {
+    std::thread worker;
+    std::atomic<int> recorded{0};
+    int rc = 0;
+    std::string err;
+    ~UploadJob() {
+        if (worker.joinable()) worker.join();
+    }
+};
+
 // resident corpus shard + per-document statistics
 struct Corpus {
     int64_t D = 0;       // global documents
@@ -64,6 +80,7 @@ struct Corpus {
     // range, recorded when that range's ids are in place
     std::vector<cudaEvent_t> range_ev;  // one per sub-range (sub_begin)
     bool ind_deferred = false;
+    std::shared_ptr<UploadJob> job;     // set while a host thread feeds the deferred ids from pageable memory
     double n_global = 0;  // sum of all values of the (global) matrix: wordsInCorpus contribution, lda.go:481
     // where the entries come from (the caller's arrays, valid for the duration of the call) and the local indptr: data
     // movement can be issued per range of local documents (upload_part)
@@ -124,8 +141,10 @@ struct lda_b200_handle {
     size_t partials_cap = 0;
     bool deterministic = false;  // sufficient statistics accumulated in 64-bit fixed point (lda_b200_set_deterministic)
     // documents per warp of the 64 < K <= 256 kernels: 1 = scvb0_docs32_kernel, 2 / 4 = scvb0_docsg_kernel
-    // (LDA_B200_DOCS_PER_WARP_FIT / LDA_B200_DOCS_PER_WARP_TRANSFORM override the defaults)
-    int docs_per_warp_fit = 1, docs_per_warp_transform = 1;
+    // (LDA_B200_DOCS_PER_WARP_FIT / LDA_B200_DOCS_PER_WARP_TRANSFORM override the defaults).  Measured at K = 256 on
+    // 65,536-document Transform ranges: 29.7 / 27.0 / 26.1 ms for 1 / 2 / 4; the fit launch, bound by the L2's reduction
+    // throughput, does not move (53.1 / 52.4 / 53.5 ms per iteration), so it keeps one document per warp.
+    int docs_per_warp_fit = 1, docs_per_warp_transform = 4;
     unsigned long long *hat_fx = nullptr;
     void *stage = nullptr;
     size_t stage_bytes = 0;
@@ -179,7 +198,7 @@ struct lda_b200_handle {
     std::string nvls_note;
 
     // stats
-    int64_t launches = 0;
+    std::atomic<int64_t> launches{0};
     bool profiling = false;
     std::vector<EventPair> ev_pool;
     size_t ev_used = 0;
@@ -275,6 +294,8 @@ void dfree(lda_b200_handle *h, T **p) {
 }
 
 void free_corpus(lda_b200_handle *h, Corpus &c) {
+    if (c.job && c.job->worker.joinable()) c.job->worker.join();
+    c.job.reset();
     if (c.ind_deferred && h->copy_stream) cudaStreamSynchronize(h->copy_stream);
     for (cudaEvent_t e : c.range_ev) cudaEventDestroy(e);
     dfree(h, &c.doc_ptr);
@@ -1195,12 +1216,37 @@ int upload_corpus(lda_b200_handle *h, Corpus &c, int64_t W, int64_t D, const int
         CU(cudaEventRecord(h->copy_ev, h->stream));
         CU(cudaStreamWaitEvent(h->copy_stream, h->copy_ev, 0));
         for (size_t si = 0; si < c.sub_begin.size(); ++si) {
-            const int64_t l0 = c.sub_begin[si];
-            TRY(upload_part(h, c, l0, std::min({Dl, l0 + c.sub, (l0 / range + 1) * range}), h->copy_stream, false, true));
             cudaEvent_t e;
             CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c.range_ev.push_back(e);
-            CU(cudaEventRecord(e, h->copy_stream));
+        }
+        auto feed = [h, &c, range, Dl](UploadJob *job) -> int {
+            for (size_t si = 0; si < c.sub_begin.size(); ++si) {
+                const int64_t l0 = c.sub_begin[si];
+                TRY(upload_part(h, c, l0, std::min({Dl, l0 + c.sub, (l0 / range + 1) * range}), h->copy_stream, false, true));
+                CU(cudaEventRecord(c.range_ev[si], h->copy_stream));
+                if (job) job->recorded.store((int)si + 1, std::memory_order_release);
+            }
+            return 0;
+        };
+        if (!c.src_device && c.nnz > 0 && is_pageable(c.src_ind)) {
+            // pageable source: every 64 MB slot is a host memcpy before its transfer; a worker thread does that while
+            // the caller's thread goes on to queue the launches (c lives in the handle for the whole fit)
+            c.job = std::make_shared<UploadJob>();
+            UploadJob *job = c.job.get();
+            const int n_sub = (int)c.sub_begin.size();
+            job->worker = std::thread([h, job, feed, n_sub]() {
+                cudaSetDevice(h->device);
+                std::string saved = h->err;
+                job->rc = feed(job);
+                if (job->rc) {
+                    job->err = h->err;  // fail() wrote the text into the handle; hand it over and let the caller report it
+                    h->err = saved;
+                }
+                job->recorded.store(n_sub, std::memory_order_release);  // nobody waits for events that will never come
+            });
+        } else {
+            TRY(feed(nullptr));
         }
         c.ind_deferred = true;
         pt.lap("ingest: word ids queued on the copy stream");
@@ -2080,8 +2126,11 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                     const int64_t s1 = std::min(r1, s0 + piece);
                     if (c.ind_deferred) {
                         const size_t i0 = (size_t)(std::lower_bound(c.sub_begin.begin(), c.sub_begin.end(), s0) - c.sub_begin.begin());
-                        for (size_t i = i0; i < c.sub_begin.size() && c.sub_begin[i] < s1; ++i)
+                        for (size_t i = i0; i < c.sub_begin.size() && c.sub_begin[i] < s1; ++i) {
+                            if (c.job)  // the event must have been recorded by the feeding thread before it can be waited on
+                                while (c.job->recorded.load(std::memory_order_acquire) <= (int)i) std::this_thread::yield();
                             CU(cudaStreamWaitEvent(h->stream, c.range_ev[i], 0));
+                        }
                     }
                     if (s0 > r0) CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
                     a.doc_begin = (int)s0;
@@ -2207,6 +2256,17 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
         }
         if (h->fitc.ind_deferred) {  // every range has been waited for; report ids that were out of range
             h->fitc.ind_deferred = false;
+            if (h->fitc.job) {
+                if (h->fitc.job->worker.joinable()) h->fitc.job->worker.join();
+                const int jrc = h->fitc.job->rc;
+                const std::string jerr = h->fitc.job->err;
+                h->fitc.job.reset();
+                if (jrc) {
+                    h->fitted = false;
+                    h->err = jerr;
+                    return jrc;
+                }
+            }
             int bad = 0;
             CU(cudaMemcpyAsync(&bad, h->err_flag, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
             CU(cudaStreamSynchronize(h->stream));
@@ -2748,7 +2808,7 @@ int lda_b200_csr_to_csc(lda_b200_handle *h, int64_t W, int64_t D, const int64_t 
     return rc;
 }
 
-int64_t lda_b200_launch_count(const lda_b200_handle *h) { return h ? h->launches : 0; }
+int64_t lda_b200_launch_count(const lda_b200_handle *h) { return h ? h->launches.load() : (int64_t)0; }
 
 int lda_b200_last_kernel_time(const lda_b200_handle *h, float *minibatch_ms, int32_t *minibatch_launches,
                               float *blend_ms, int32_t *blend_launches) {
