@@ -987,17 +987,28 @@ __global__ void __launch_bounds__(256) nvls_reduce_blend_kernel(const FusedArgs 
     const int64_t stride = (int64_t)gridDim.x * RPB;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const float4 *nphi_local = reinterpret_cast<const float4 *>(a.pt.nphi[me]);
-    for (int64_t r0 = a.row0 + (int64_t)blockIdx.x * RPB + rslot; r0 < a.row1; r0 += stride * U) {
-        float4 sum[U], p[U];
+    // Software pipeline: the reductions of batch i+1 are requested before the results of batch i are stored, so that the
+    // inbound (ld_reduce) and outbound (st) halves of the NVLink traffic can overlap.  (Measured on 2 GPUs, 51 MB per
+    // direction and phase: reductions alone 0.13 ms, stores alone 0.11 ms, both 0.27-0.28 ms with or without the pipeline
+    // and for 1, 2 or 4 blocks per SM -- the two halves share a limit of about 370 GB/s per direction, which is also what
+    // ncclAllReduce reaches through the same NVLS path at its best message size.)
+    float4 sum[U], p[U], nsum[U], np[U];
+    auto request = [&](int64_t r0, float4 (&s_)[U], float4 (&p_)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t r = r0 + u * stride;
             if (r < a.row1) {
                 const int64_t e = r * VPR + col;  // float4 index
-                sum[u] = multimem_ld_reduce_add(a.mc_hat + 4 * e);  // U reductions in flight per thread
-                p[u] = nphi_local[e];
+                s_[u] = multimem_ld_reduce_add(a.mc_hat + 4 * e);
+                p_[u] = nphi_local[e];
             }
         }
+    };
+    int64_t r0 = a.row0 + (int64_t)blockIdx.x * RPB + rslot;
+    if (r0 < a.row1) request(r0, sum, p);
+    for (; r0 < a.row1; r0 += stride * U) {
+        const int64_t rn = r0 + stride * U;
+        if (rn < a.row1) request(rn, nsum, np);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t r = r0 + u * stride;
@@ -1014,6 +1025,11 @@ __global__ void __launch_bounds__(256) nvls_reduce_blend_kernel(const FusedArgs 
                 acc.z += sum[u].z;
                 acc.w += sum[u].w;
             }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            sum[u] = nsum[u];
+            p[u] = np[u];
         }
     }
     // zero the buffer the next step accumulates into (its readers finished at the previous step's closing barrier)

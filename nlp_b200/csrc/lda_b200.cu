@@ -2182,14 +2182,16 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 fa.Kp = h->Kp;
                 fa.A = (float)Ad;
                 fa.C = (float)Cd;
-                TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
+                // blocks of the exchange kernel: the multicast variant runs fewer threads with several pipelined batches each
+                const int xgrid = h->nvls.active ? h->sms : h->sms * 4;
+                TRY(ensure_partials(h, (size_t)xgrid * h->Kp));
                 fa.partials = h->partials;
                 fa.mc_hat = h->mc_hat[h->hat_cur];
                 fa.mc_nphi = h->mc_nphi;
                 const int bs = blend_block(h->Kp);
                 TRY(ev_begin(h, 4, &ph));
                 if (h->nvls.active)
-                    nvls_reduce_blend_kernel<4><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
+                    nvls_reduce_blend_kernel<2><<<xgrid, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 else if (R <= 2)
                     peer_reduce_blend_kernel<4, 2><<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(fa);
                 else if (R <= 4)
@@ -2199,7 +2201,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 KCHECK();
                 TRY(ev_end(h, ph));
                 TRY(ev_begin(h, 5, &ph));
-                TRY(reduce_partials(h, h->sms * 4, h->Kp, h->nzhat, false, h->stream));  // this rank's share of nZHat
+                TRY(reduce_partials(h, xgrid, h->Kp, h->nzhat, false, h->stream));  // this rank's share of nZHat
                 bar.finish = 1;
                 bar.epoch = ++h->epoch;
                 xgpu_barrier_kernel<<<1, 256, 0, h->stream>>>(bar);
