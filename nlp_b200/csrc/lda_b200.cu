@@ -2062,6 +2062,7 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
     const int64_t nsteps = (M + G - 1) / G;
     const int B = cfg.burn_in_passes;
     int evals = 0, ran = 0;
+    std::vector<double> coef;  // c_g of the current step (see below)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (elapsed_ms) {
         CU(cudaEventCreate(&e0));
@@ -2087,12 +2088,20 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
             const int n_s = (int)std::min<int64_t>(G, M - s * G);
             DocsArgs a = docs_args(h, c, B);
             int64_t l_first = -1, l_last = -1;
-            double A = 1.0, c_single = 0.0;
+            // coefficients of the step in one backward pass (what lda_b200_plan_step returns for every g, same order of
+            // operations): a call per minibatch would cost n_s^2 pow() evaluations -- more than a millisecond of host time
+            // per step at n_s = 128, as long as an 8-GPU step lasts on the device
+            double A = 1.0;
+            coef.resize((size_t)n_s);
+            for (int g = n_s - 1; g >= 0; --g) {
+                const double rho = rho_calc(cfg.rho_phi, ctr->rho_phi_t + g);
+                coef[g] = rho * A;
+                A *= (1.0 - rho);
+            }
+            const double c_single = n_s > 0 ? coef[0] : 0.0;  // used only when n_s == 1; identical on every rank
             for (int g = 0; g < n_s; ++g) {
                 const int64_t m = s * G + g;
-                double cg = 0.0;
-                lda_b200_plan_step(&cfg.rho_phi, ctr->rho_phi_t, n_s, g, &A, &cg);
-                if (g == 0) c_single = cg;  // used only when n_s == 1; identical on every rank
+                const double cg = coef[g];
                 if (m % R != h->rank) continue;
                 const int64_t l = m / R;  // local minibatch index on this rank
                 if (l_first < 0) l_first = l;
