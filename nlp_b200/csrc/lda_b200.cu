@@ -133,6 +133,7 @@ struct lda_b200_handle {
     double *colsum = nullptr;
     float *inv_colsum = nullptr;
     int *doc_counter = nullptr;
+    unsigned *ticket = nullptr;  // last-block election of hat_colsum_nz_kernel (zero between launches)
     int *err_flag = nullptr;
     double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
     float *rho_tab = nullptr;
@@ -1784,6 +1785,8 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         uint64_t keep = UINT64_MAX;
         CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         TRY(dalloc(h, &h->doc_counter, 1));
+        TRY(dalloc(h, &h->ticket, 1));
+        CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
         TRY(dalloc(h, &h->err_flag, 1));
         TRY(dalloc(h, &h->dacc, 2));
         CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
@@ -1828,6 +1831,7 @@ void lda_b200_destroy(lda_b200_handle *h) {
     dfree(h, &h->inv_z);
     dfree(h, &h->inv_colsum);
     dfree(h, &h->doc_counter);
+    dfree(h, &h->ticket);
     dfree(h, &h->err_flag);
     dfree(h, &h->dacc);
     dfree(h, &h->rho_tab);
@@ -2243,11 +2247,11 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 const int bs = blend_block(h->Kp);
                 int slot;
                 TRY(ev_begin(h, 1, &slot));
-                TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
-                hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->partials);
-                KCHECK();
-                nz_update_kernel<<<1, 1024, 0, h->stream>>>(h->nz, h->partials, h->sms * 4, h->inv_z, h->doc_counter, h->K, h->Kp, Ad, Cd,
-                                                           cfg.eta * (double)h->W);
+                // column sums of nPhiHat (nZHat), nZ' and invZ' in one launch: the last block to finish adds the blocks' partials
+                TRY(ensure_partials(h, (size_t)h->sms * 2 * h->Kp));
+                hat_colsum_nz_kernel<8><<<h->sms * 2, bs, (size_t)bs * sizeof(float4), h->stream>>>(
+                    h->nphi_hat, h->W, h->Kp, h->partials, h->ticket, h->nz, h->inv_z, h->doc_counter, h->K, Ad, Cd,
+                    cfg.eta * (double)h->W);
                 KCHECK();
                 BlendArgs ba;
                 ba.nphi = h->nphi;
