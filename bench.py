@@ -515,10 +515,14 @@ def parity_leg(args, new_lda, rank, world, dev, W, K, md):
         indptr, ind, data = corpus_synth.generate(n_s, W, block=bs, mean_distinct=md, device=dev)
         sub = CSC(W, n_s, indptr, ind, data)
         f = dict(Iterations=2, BatchSize=bs, PerplexityEvaluationFrequency=1, PerplexityTolerance=0.0)
+        # the sample is small, and small launch ranges would take the latency-optimised (two tokens per butterfly) kernels:
+        # keep the parity leg on the kernels the timed run used (the handle reads the variable when it is created)
+        os.environ["LDA_B200_PAIR_MAX_DOCS"] = "0"
         a = new_lda(2, processes=procs, batch=bs)
         for k_, v_ in f.items():
             setattr(a, k_, v_)
         got = a.FitTransform(sub)
+        os.environ.pop("LDA_B200_PAIR_MAX_DOCS", None)
         trace = list(a.PerplexityTrace)
         path = a.CommInfo()[2]
         a.Close()

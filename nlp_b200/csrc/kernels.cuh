@@ -79,6 +79,7 @@ struct DocsArgs {
     // fx_scale a power of two), whose atomic sums do not depend on the order in which the warps arrive
     unsigned long long *hat_fx;  // [W][Kp]
     float fx_scale;
+    int pair;                // host-side hint: the launch range is small, use the two-tokens-per-butterfly kernel (PAIR)
 };
 constexpr int MAX_CONCURRENT_MB = 256;
 
@@ -286,8 +287,15 @@ constexpr int docs32_ring_rows(int NV) { return NV == 1 ? 8 : NV == 2 ? 6 : NV =
 constexpr int docs32_min_blocks(int NV) { return NV <= 2 ? 4 : NV == 4 ? 2 : 1; }
 constexpr int docs32_smem_bytes(int NV) { return 8 * docs32_ring_rows(NV) * NV * 512; }
 
-template <int NV, bool FULLK, bool FIT, bool DET = false>
-__global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
+// PAIR: two tokens per shuffle tree.  The normaliser of token t+1 is affine in the normaliser of token t,
+//   S' = sum_k c'_k theta'_k,  theta'_k = theta_k (keep + mix c_k) + alpha q   =>   S' = keep Y + mix X + alpha q Z,
+//   Y = sum c'_k theta_k,  X = sum c'_k c_k theta_k,  Z = sum c'_k   (mix = q wc / S, the only term that needs S),
+// so S, Y, X and Z ride one butterfly and the dependent chain per token -- what bounds a launch of few documents, which lasts
+// as long as its longest document -- is about half as long, for a fifth more instructions.  Same values up to fp32
+// rounding of the regrouped sum (all terms are non-negative: no cancellation).  Used for launches too small to fill the
+// device (lda_b200.cu: pair_docs_max).
+template <int NV, bool FULLK, bool FIT, bool DET = false, bool PAIR = false>
+__global__ void __launch_bounds__(256, PAIR ? (NV <= 2 ? 2 : 1) : docs32_min_blocks(NV)) scvb0_docs32_kernel(const DocsArgs a, const int *__restrict__ order) {
     constexpr int R = docs32_ring_rows(NV);
     extern __shared__ float4 ring_all[];
     const int lane = threadIdx.x & 31;
@@ -396,9 +404,8 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
             if (ti == 0 && chk && 1 < passes) prev = theta_sum();  // lda.go:224-230
 
             const int ntile = min(32, len - (ti << 5));
-            auto run_tile = [&](auto is_main) {
-            constexpr bool MAINP = decltype(is_main)::value;
-            for (int t = 0; t < ntile; ++t) {
+            auto one_token = [&](auto is_main, int t) {
+                constexpr bool MAINP = decltype(is_main)::value;
                 const float qt = __shfl_sync(FULL, cur.q, t);
                 const int wn = __shfl_sync(FULL, cur.la, t);
                 cp_async_wait<R - 1>();  // the oldest outstanding group (this token's row) has landed
@@ -442,7 +449,107 @@ __global__ void __launch_bounds__(256, docs32_min_blocks(NV)) scvb0_docs32_kerne
                     tha[v].z = fmaf(tha[v].z, fmaf(mix, c[v].z, keep), aq);
                     tha[v].w = fmaf(tha[v].w, fmaf(mix, c[v].w, keep), aq);
                 }
-            }
+            };
+            // tokens t and t+1 of the current tile with one butterfly (see PAIR above)
+            auto two_tokens = [&](auto is_main, int t) {
+                constexpr bool MAINP = decltype(is_main)::value;
+                const float qa = __shfl_sync(FULL, cur.q, t), qb = __shfl_sync(FULL, cur.q, t + 1);
+                const int wna = __shfl_sync(FULL, cur.la, t), wnb = __shfl_sync(FULL, cur.la, t + 1);
+                const int slot_b = slot + 1 == R ? 0 : slot + 1;
+                cp_async_wait<R - 2>();  // the two oldest outstanding groups (the rows of t and t+1) have landed
+                float4 ca[NV], cb[NV], u[NV];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    ca[v] = ok[v] ? ring[(slot * NV + v) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    cb[v] = ok[v] ? ring[(slot_b * NV + v) * 32] : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                issue(slot, wna);
+                issue(slot_b, wnb);
+                slot = slot_b + 1 == R ? 0 : slot_b + 1;
+
+                float s0 = 0.f, s1 = 0.f, y0 = 0.f, y1 = 0.f, x0 = 0.f, x1 = 0.f, z0 = 0.f, z1 = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    u[v] = make_float4(ca[v].x * tha[v].x, ca[v].y * tha[v].y, ca[v].z * tha[v].z, ca[v].w * tha[v].w);
+                    s0 += u[v].x;
+                    s1 += u[v].y;
+                    s0 += u[v].z;
+                    s1 += u[v].w;
+                    y0 = fmaf(cb[v].x, tha[v].x, y0);
+                    y1 = fmaf(cb[v].y, tha[v].y, y1);
+                    y0 = fmaf(cb[v].z, tha[v].z, y0);
+                    y1 = fmaf(cb[v].w, tha[v].w, y1);
+                    x0 = fmaf(cb[v].x, u[v].x, x0);
+                    x1 = fmaf(cb[v].y, u[v].y, x1);
+                    x0 = fmaf(cb[v].z, u[v].z, x0);
+                    x1 = fmaf(cb[v].w, u[v].w, x1);
+                    z0 += cb[v].x + cb[v].z;
+                    z1 += cb[v].y + cb[v].w;
+                }
+                float Sa = s0 + s1, Y = y0 + y1, X = x0 + x1, Z = z0 + z1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {  // four independent sums per level
+                    Sa += __shfl_xor_sync(FULL, Sa, o);
+                    Y += __shfl_xor_sync(FULL, Y, o);
+                    X += __shfl_xor_sync(FULL, X, o);
+                    Z += __shfl_xor_sync(FULL, Z, o);
+                }
+                const float ra = fast_rcp(Sa);
+                const float keepa = 1.0f - qa, mixa = qa * wcj * ra, aqa = alpha * qa;
+                const float Sb = fmaf(mixa, X, fmaf(keepa, Y, aqa * Z));
+                const float rb = fast_rcp(Sb);
+                const float keepb = 1.0f - qb, mixb = qb * wcj * rb, aqb = alpha * qb;
+                if (MAINP) {
+                    const int w = __shfl_sync(FULL, cur.wi, t);
+                    const float sc = hat_scale * ra;
+                    const size_t hoff = (size_t)((unsigned)w * row_vecs + lane_vec) * 4u;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (ok[v]) {
+                            const float4 add = make_float4(sc * u[v].x, sc * u[v].y, sc * u[v].z, sc * u[v].w);
+                            if (DET)
+                                red_add_fx4(a.hat_fx + hoff + 128 * v, add, a.fx_scale);
+                            else
+                                red_add_v4(a.nphi_hat + hoff + 128 * v, add);
+                        }
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    tha[v].x = fmaf(tha[v].x, fmaf(mixa, ca[v].x, keepa), aqa);
+                    tha[v].y = fmaf(tha[v].y, fmaf(mixa, ca[v].y, keepa), aqa);
+                    tha[v].z = fmaf(tha[v].z, fmaf(mixa, ca[v].z, keepa), aqa);
+                    tha[v].w = fmaf(tha[v].w, fmaf(mixa, ca[v].w, keepa), aqa);
+                }
+                if (MAINP) {
+                    const int w = __shfl_sync(FULL, cur.wi, t + 1);
+                    const float sc = hat_scale * rb;
+                    const size_t hoff = (size_t)((unsigned)w * row_vecs + lane_vec) * 4u;
+#pragma unroll
+                    for (int v = 0; v < NV; ++v)
+                        if (ok[v]) {
+                            const float4 add = make_float4(sc * cb[v].x * tha[v].x, sc * cb[v].y * tha[v].y, sc * cb[v].z * tha[v].z,
+                                                           sc * cb[v].w * tha[v].w);
+                            if (DET)
+                                red_add_fx4(a.hat_fx + hoff + 128 * v, add, a.fx_scale);
+                            else
+                                red_add_v4(a.nphi_hat + hoff + 128 * v, add);
+                        }
+                }
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    tha[v].x = fmaf(tha[v].x, fmaf(mixb, cb[v].x, keepb), aqb);
+                    tha[v].y = fmaf(tha[v].y, fmaf(mixb, cb[v].y, keepb), aqb);
+                    tha[v].z = fmaf(tha[v].z, fmaf(mixb, cb[v].z, keepb), aqb);
+                    tha[v].w = fmaf(tha[v].w, fmaf(mixb, cb[v].w, keepb), aqb);
+                }
+            };
+            auto run_tile = [&](auto is_main) {
+                int t = 0;
+                if constexpr (PAIR) {
+                    static_assert(!PAIR || R >= 3, "two rows are consumed per step");
+                    for (; t + 1 < ntile; t += 2) two_tokens(is_main, t);
+                }
+                for (; t < ntile; ++t) one_token(is_main, t);
             };
             if (FIT && !burn)
                 run_tile(std::true_type{});

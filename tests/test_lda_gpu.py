@@ -791,3 +791,26 @@ def test_step_issued_as_sub_range_launches(monkeypatch):
         assert np.abs(got - want).max() <= THETA_ATOL
         lda2 = new_lda(k, Processes=procs, **f)                       # pageable result: no streaming out, same answer
         assert np.abs(lda2.FitTransform(m) - want).max() <= THETA_ATOL
+
+
+@pytest.mark.parametrize("k,D,W,b", [(100, 300, 800, 100), (200, 120, 600, 32), (256, 300, 1000, 128), (500, 60, 500, 32),
+                                     (1024, 48, 400, 16)])
+def test_throughput_kernels_on_small_corpora(k, D, W, b, monkeypatch):
+    """Launch ranges of up to LDA_B200_PAIR_MAX_DOCS documents (default 8,192) run the two-tokens-per-butterfly kernels, so every
+    small-corpus test above exercises those; this one switches them off and checks the kernels large launches use (one token
+    per butterfly, and for Transform at 64 < K <= 256 four documents per warp) against the oracle on the same small corpora,
+    fit and Transform, and the two variants against each other."""
+    monkeypatch.setenv("LDA_B200_PAIR_MAX_DOCS", "0")
+    m = synth(D, W, 40, block=b)
+    lda, o = run_pair(m, k, 4, BatchSize=b)
+    held = synth(80, W, 40, block=b, seed=4242)
+    o.set_state(*lda.GetState())
+    t, passes = lda.Transform(held, return_passes=True)
+    t_want, p_want = o.Transform(tuple(held), return_passes=True)
+    same = passes == p_want
+    assert same.mean() >= 0.9 and np.abs(t - t_want)[:, same].max() <= THETA_ATOL
+    monkeypatch.delenv("LDA_B200_PAIR_MAX_DOCS")
+    nphi_unpaired = lda.GetState()[0]
+    paired, _ = run_pair(m, k, 4, BatchSize=b)   # default: this launch size takes the paired kernels
+    nphi_paired = paired.GetState()[0]
+    assert np.abs(nphi_paired - nphi_unpaired).max() <= 1e-4 * max(1.0, np.abs(nphi_unpaired).max())
