@@ -35,9 +35,7 @@ out = {"docs": a.docs, "K": K, "batch_size": a.batch, "doc_len_mean": float(lens
 
 
 def run(batch, procs, pair_max=None):
-    if pair_max is None:
-        os.environ.pop("LDA_B200_PAIR_MAX_DOCS", None)
-    else:
+    if pair_max is not None:   # otherwise whatever the caller's environment says (default: the library's own threshold)
         os.environ["LDA_B200_PAIR_MAX_DOCS"] = str(pair_max)   # read when the handle is created
     lda = nlp_b200.NewLatentDirichletAllocation(K, device=0)
     lda.Rnd = rand.New(rand.NewSource(0))
