@@ -984,7 +984,10 @@ int ensure_pin_ring(lda_b200_handle *h) {
         CU(cudaMallocHost(&h->pin_slot[i], lda_b200_handle::kStageSlotBytes));
         CU(cudaEventCreateWithFlags(&h->pin_done[i], cudaEventDisableTiming));
     }
-    h->host_threads = (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency() / 2));
+    // staging copies between pageable caller memory and the page-locked ring scale with the number of copying threads up to
+    // the host's hardware threads (a single thread moves 1-2.5 GB/s); the ranks of a multi-GPU job share them
+    h->host_threads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency() / (unsigned)std::max(1, h->nranks)));
+    if (const char *e = getenv("LDA_B200_HOST_THREADS")) h->host_threads = std::max(1, atoi(e));
     return 0;
 }
 
