@@ -796,10 +796,10 @@ def test_step_issued_as_sub_range_launches(monkeypatch):
 @pytest.mark.parametrize("k,D,W,b", [(100, 300, 800, 100), (200, 120, 600, 32), (256, 300, 1000, 128), (500, 60, 500, 32),
                                      (1024, 48, 400, 16)])
 def test_throughput_kernels_on_small_corpora(k, D, W, b, monkeypatch):
-    """Launch ranges of up to LDA_B200_PAIR_MAX_DOCS documents (default 8,192) run the two-tokens-per-butterfly kernels, so every
-    small-corpus test above exercises those; this one switches them off and checks the kernels large launches use (one token
-    per butterfly, and for Transform at 64 < K <= 256 four documents per warp) against the oracle on the same small corpora,
-    fit and Transform, and the two variants against each other."""
+    """Launch ranges of up to LDA_B200_PAIR_MAX_DOCS documents run the two-tokens-per-butterfly kernels, larger ones the
+    throughput kernels (one token per butterfly, and for Transform at 64 < K <= 256 four documents per warp).  Whatever the
+    default threshold is, this test runs both families on the same small corpora -- fit and Transform against the oracle, and
+    the two fitted models against each other."""
     monkeypatch.setenv("LDA_B200_PAIR_MAX_DOCS", "0")
     m = synth(D, W, 40, block=b)
     lda, o = run_pair(m, k, 4, BatchSize=b)
@@ -809,8 +809,13 @@ def test_throughput_kernels_on_small_corpora(k, D, W, b, monkeypatch):
     t_want, p_want = o.Transform(tuple(held), return_passes=True)
     same = passes == p_want
     assert same.mean() >= 0.9 and np.abs(t - t_want)[:, same].max() <= THETA_ATOL
-    monkeypatch.delenv("LDA_B200_PAIR_MAX_DOCS")
+    monkeypatch.setenv("LDA_B200_PAIR_MAX_DOCS", "8192")
     nphi_unpaired = lda.GetState()[0]
-    paired, _ = run_pair(m, k, 4, BatchSize=b)   # default: this launch size takes the paired kernels
+    paired, o2 = run_pair(m, k, 4, BatchSize=b)   # this launch size now takes the paired kernels
+    o2.set_state(*paired.GetState())
+    t2, passes2 = paired.Transform(held, return_passes=True)
+    t2_want, p2_want = o2.Transform(tuple(held), return_passes=True)
+    same2 = passes2 == p2_want
+    assert same2.mean() >= 0.9 and np.abs(t2 - t2_want)[:, same2].max() <= THETA_ATOL
     nphi_paired = paired.GetState()[0]
     assert np.abs(nphi_paired - nphi_unpaired).max() <= 1e-4 * max(1.0, np.abs(nphi_unpaired).max())
