@@ -859,6 +859,70 @@ __global__ void hat_fx_to_float_kernel(unsigned long long *fx, float *hat, int64
     }
 }
 
+// the two-launch form of the column sums + nZ update (LDA_B200_FUSED_NZ=0): per-block column sums, then one block adds them
+__global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64_t W, int Kp, double *partials) {
+    extern __shared__ float4 sm4[];
+    const int VPR = Kp >> 2;
+    const int RPB = blockDim.x / VPR;
+    const int col = threadIdx.x % VPR;
+    const int rslot = threadIdx.x / VPR;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t r = (int64_t)blockIdx.x * RPB + rslot; r < W; r += (int64_t)gridDim.x * RPB) {
+        const float4 h = reinterpret_cast<const float4 *>(hat + r * Kp)[col];
+        acc.x += h.x;
+        acc.y += h.y;
+        acc.z += h.z;
+        acc.w += h.w;
+    }
+    sm4[threadIdx.x] = acc;
+    __syncthreads();
+    if (rslot == 0) {
+        double sx = 0, sy = 0, sz = 0, sw = 0;
+        for (int s = 0; s < RPB; ++s) {
+            const float4 t = sm4[s * VPR + col];
+            sx += t.x;
+            sy += t.y;
+            sz += t.z;
+            sw += t.w;
+        }
+        double *p = partials + (size_t)blockIdx.x * Kp + 4 * col;
+        p[0] = sx;
+        p[1] = sy;
+        p[2] = sz;
+        p[3] = sw;
+    }
+}
+
+// launched as one block of 1024 threads: four threads share a topic, each adds every fourth block's partial sum (eight
+// loads in flight), and the four shares are combined in a fixed order -- the result does not depend on timing
+__global__ void __launch_bounds__(1024) nz_update_kernel(double *nz, const double *partials, int nblocks, float *inv_z, int *doc_counter,
+                                                         int K, int Kp, double Ad, double Cd, double etaW) {
+    __shared__ double share[4][256];
+    const int lane_k = threadIdx.x & 255, part = threadIdx.x >> 8;
+    for (int k0 = 0; k0 < Kp; k0 += 256) {
+        const int k = k0 + lane_k;
+        double s = 0;
+        if (k < K) {
+#pragma unroll 8
+            for (int b = part; b < nblocks; b += 4) s += partials[(size_t)b * Kp + k];
+        }
+        share[part][lane_k] = s;
+        __syncthreads();
+        if (part == 0 && k < Kp) {
+            if (k < K) {
+                const double zhat = ((share[0][lane_k] + share[1][lane_k]) + share[2][lane_k]) + share[3][lane_k];  // nZHat[k]
+                const double z = Ad * nz[k] + Cd * zhat;
+                nz[k] = z;
+                inv_z[k] = (float)(1.0 / (z + etaW));
+            } else {
+                inv_z[k] = 0.f;
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *doc_counter = 0;
+}
+
 // Column sums of nPhiHat and the nZ update as one launch (single-GPU and ncclAllReduce paths): every block stores its partial
 // column sums; the block that takes the last ticket adds all partials in block order (four interleaved accumulators
 // combined in a fixed order, so the result does not depend on which block came last) and applies lda.go:313-317.

@@ -136,6 +136,7 @@ struct lda_b200_handle {
     float *inv_colsum = nullptr;
     int *doc_counter = nullptr;
     int64_t pair_docs_max = 0;  // launch ranges up to this many documents use the PAIR kernels (LDA_B200_PAIR_MAX_DOCS); 0 = off
+    bool fused_nz = false;  // hat_colsum_nz_kernel instead of hat_colsum_kernel + nz_update_kernel (LDA_B200_FUSED_NZ)
     unsigned *ticket = nullptr;  // last-block election of hat_colsum_nz_kernel (zero between launches)
     int *err_flag = nullptr;
     double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
@@ -1820,6 +1821,7 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
             return (v == 1 || v == 2 || v == 4) ? v : dflt;
         };
         if (const char *e = getenv("LDA_B200_PAIR_MAX_DOCS")) h->pair_docs_max = atoll(e);
+        if (const char *e = getenv("LDA_B200_FUSED_NZ")) h->fused_nz = atoi(e) != 0;
         h->docs_per_warp_fit = env_gd("LDA_B200_DOCS_PER_WARP_FIT", h->docs_per_warp_fit);
         h->docs_per_warp_transform = env_gd("LDA_B200_DOCS_PER_WARP_TRANSFORM", h->docs_per_warp_transform);
         h->stage_bytes = (size_t)256 << 20;
@@ -2272,12 +2274,21 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 const int bs = blend_block(h->Kp);
                 int slot;
                 TRY(ev_begin(h, 1, &slot));
-                // column sums of nPhiHat (nZHat), nZ' and invZ' in one launch: the last block to finish adds the blocks' partials
-                TRY(ensure_partials(h, (size_t)h->sms * 2 * h->Kp));
-                hat_colsum_nz_kernel<8><<<h->sms * 2, bs, (size_t)bs * sizeof(float4), h->stream>>>(
-                    h->nphi_hat, h->W, h->Kp, h->partials, h->ticket, h->nz, h->inv_z, h->doc_counter, h->K, Ad, Cd,
-                    cfg.eta * (double)h->W);
-                KCHECK();
+                if (h->fused_nz) {
+                    // column sums of nPhiHat (nZHat), nZ' and invZ' in one launch: the last block to finish adds the partials
+                    TRY(ensure_partials(h, (size_t)h->sms * 2 * h->Kp));
+                    hat_colsum_nz_kernel<8><<<h->sms * 2, bs, (size_t)bs * sizeof(float4), h->stream>>>(
+                        h->nphi_hat, h->W, h->Kp, h->partials, h->ticket, h->nz, h->inv_z, h->doc_counter, h->K, Ad, Cd,
+                        cfg.eta * (double)h->W);
+                    KCHECK();
+                } else {
+                    TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
+                    hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->partials);
+                    KCHECK();
+                    nz_update_kernel<<<1, 1024, 0, h->stream>>>(h->nz, h->partials, h->sms * 4, h->inv_z, h->doc_counter, h->K, h->Kp,
+                                                               Ad, Cd, cfg.eta * (double)h->W);
+                    KCHECK();
+                }
                 BlendArgs ba;
                 ba.nphi = h->nphi;
                 ba.nphi_hat = h->nphi_hat;
