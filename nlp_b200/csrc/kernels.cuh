@@ -818,10 +818,12 @@ __global__ void rho_table_kernel(double S, double Tau, double Kappa, double t0, 
     if (c < n) out[c] = (float)log1p(-S / pow(Tau + t0 + (double)c, Kappa));
 }
 
-// M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58), as two launches on the stream:
-//   hat_colsum_nz_kernel : nZHat[k] = sum_w nPhiHat[w,k] (== the reference's running sum, lda.go:295), per block; the last block
-//                          adds the blocks' sums in block order ; nZ = A nZ + C nZHat ; invZ = 1/(nZ + eta W) ; scheduler reset
-//   phi_blend_kernel     : nPhi = A nPhi + C nPhiHat ; nPhiHat = 0 ; c = (nPhi + eta) invZ            (lda.go:303-310)
+// M step (lda.go:303-317) fused with ldaMiniBatch.reset (lda.go:50-58), as three launches on the stream:
+//   hat_colsum_kernel : nZHat[k] = sum_w nPhiHat[w,k]   (== the reference's running sum, lda.go:295)
+//   nz_update_kernel  : nZHat = sum of the per-block sums ; nZ = A nZ + C nZHat ; invZ = 1/(nZ + eta W) ; scheduler reset (lda.go:313-317)
+//   phi_blend_kernel  : nPhi = A nPhi + C nPhiHat ; nPhiHat = 0 ; c = (nPhi + eta) invZ            (lda.go:303-310)
+// (A one-launch form of the first two -- the block that takes the last ticket adds the partials -- was measured and is slower:
+//  0.139 vs 0.126 ms per M-step at C3; one block reading every partial costs more than the second launch.)
 // blockDim.x = VPR*RPB with VPR = Kp/4 float4 per row, so a thread always owns the same 4 topics.
 // Cross-block sums (column sums, perplexity, word counts) are taken in two steps so that they do not depend on the order
 // in which blocks finish: every block stores its partial result, sum_partials_kernel adds the blocks in index order.
@@ -859,7 +861,6 @@ __global__ void hat_fx_to_float_kernel(unsigned long long *fx, float *hat, int64
     }
 }
 
-// the two-launch form of the column sums + nZ update (LDA_B200_FUSED_NZ=0): per-block column sums, then one block adds them
 __global__ void __launch_bounds__(256) hat_colsum_kernel(const float *hat, int64_t W, int Kp, double *partials) {
     extern __shared__ float4 sm4[];
     const int VPR = Kp >> 2;
@@ -921,98 +922,6 @@ __global__ void __launch_bounds__(1024) nz_update_kernel(double *nz, const doubl
         __syncthreads();
     }
     if (threadIdx.x == 0) *doc_counter = 0;
-}
-
-// Column sums of nPhiHat and the nZ update as one launch (single-GPU and ncclAllReduce paths): every block stores its partial
-// column sums; the block that takes the last ticket adds all partials in block order (four interleaved accumulators
-// combined in a fixed order, so the result does not depend on which block came last) and applies lda.go:313-317.
-// U rows per thread are in flight, so that one block per SM is enough to stream nPhiHat and the last block has only
-// gridDim.x * Kp partials to read.
-template <int U>
-__global__ void __launch_bounds__(256) hat_colsum_nz_kernel(const float *hat, int64_t W, int Kp, double *partials, unsigned *ticket,
-                                                            double *nz, float *inv_z, int *doc_counter, int K, double Ad, double Cd,
-                                                            double etaW) {
-    extern __shared__ float4 sm4[];
-    __shared__ bool is_last;
-    const int VPR = Kp >> 2;
-    const int RPB = blockDim.x / VPR;
-    const int col = threadIdx.x % VPR;
-    const int rslot = threadIdx.x / VPR;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int64_t stride = (int64_t)gridDim.x * RPB;
-    int64_t r0 = (int64_t)blockIdx.x * RPB + rslot;
-    const float4 *src = reinterpret_cast<const float4 *>(hat) + col;
-    const int64_t vstride = stride * VPR;  // in float4
-    for (; r0 + (U - 1) * stride < W; r0 += stride * U) {  // U unconditional loads in flight per thread
-        const float4 *p = src + r0 * VPR;
-        float4 hv[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) hv[u] = p[u * vstride];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            acc.x += hv[u].x;
-            acc.y += hv[u].y;
-            acc.z += hv[u].z;
-            acc.w += hv[u].w;
-        }
-    }
-    for (; r0 < W; r0 += stride) {
-        const float4 t = src[r0 * VPR];
-        acc.x += t.x;
-        acc.y += t.y;
-        acc.z += t.z;
-        acc.w += t.w;
-    }
-    sm4[threadIdx.x] = acc;
-    __syncthreads();
-    if (rslot == 0) {
-        double sx = 0, sy = 0, sz = 0, sw = 0;
-        for (int s = 0; s < RPB; ++s) {
-            const float4 t = sm4[s * VPR + col];
-            sx += t.x;
-            sy += t.y;
-            sz += t.z;
-            sw += t.w;
-        }
-        double *p = partials + (size_t)blockIdx.x * Kp + 4 * col;
-        __stcg(p, sx);
-        __stcg(p + 1, sy);
-        __stcg(p + 2, sz);
-        __stcg(p + 3, sw);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    const int nb = (int)gridDim.x;
-    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
-        if (k < K) {
-            double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-            int b = 0;
-#pragma unroll 2
-            for (; b + 3 < nb; b += 4) {
-                s0 += __ldcg(partials + (size_t)b * Kp + k);
-                s1 += __ldcg(partials + (size_t)(b + 1) * Kp + k);
-                s2 += __ldcg(partials + (size_t)(b + 2) * Kp + k);
-                s3 += __ldcg(partials + (size_t)(b + 3) * Kp + k);
-            }
-            if (b < nb) s0 += __ldcg(partials + (size_t)b * Kp + k);
-            if (b + 1 < nb) s1 += __ldcg(partials + (size_t)(b + 1) * Kp + k);
-            if (b + 2 < nb) s2 += __ldcg(partials + (size_t)(b + 2) * Kp + k);
-            const double zhat = ((s0 + s1) + s2) + s3;  // nZHat[k]
-            const double z = Ad * nz[k] + Cd * zhat;
-            nz[k] = z;
-            inv_z[k] = (float)(1.0 / (z + etaW));
-        } else {
-            inv_z[k] = 0.f;
-        }
-    }
-    if (threadIdx.x == 0) {
-        *doc_counter = 0;
-        *ticket = 0u;  // ready for the next launch on this stream
-    }
 }
 
 struct BlendArgs {

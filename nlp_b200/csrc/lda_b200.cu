@@ -7,7 +7,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/mman.h>
 #include <time.h>
 #include <unistd.h>
 
@@ -135,9 +134,7 @@ struct lda_b200_handle {
     double *colsum = nullptr;
     float *inv_colsum = nullptr;
     int *doc_counter = nullptr;
-    int64_t pair_docs_max = 0;  // launch ranges up to this many documents use the PAIR kernels (LDA_B200_PAIR_MAX_DOCS); 0 = off
-    bool fused_nz = false;  // hat_colsum_nz_kernel instead of hat_colsum_kernel + nz_update_kernel (LDA_B200_FUSED_NZ)
-    unsigned *ticket = nullptr;  // last-block election of hat_colsum_nz_kernel (zero between launches)
+    int64_t pair_docs_max = 16384;  // launch ranges up to this many documents use the PAIR kernels (LDA_B200_PAIR_MAX_DOCS; 0 = never)
     int *err_flag = nullptr;
     double *dacc = nullptr;  // [2]: perplexity accumulator, N accumulator
     float *rho_tab = nullptr;
@@ -967,18 +964,6 @@ void threaded_memcpy(void *dst, const void *src, size_t bytes, int threads) {
     for (std::thread &t : pool) t.join();
 }
 
-// A result the caller has just allocated (np.zeros, make([]float64, n)) is untouched anonymous memory: asking for huge pages
-// before the first write makes the kernel fault it in 2 MB at a time, and the host copy into it runs about twice as fast
-// (measured: 1 GB by 8 threads into fresh pages 119 ms, 56-74 ms after the advice).  Advisory only: contents and
-// semantics are unchanged, pages that already exist are not affected; LDA_B200_NO_MADVISE=1 switches it off.
-void advise_huge_pages(void *p, size_t bytes) {
-    static const bool off = getenv("LDA_B200_NO_MADVISE") != nullptr;
-    if (off || bytes < ((size_t)8 << 20)) return;
-    const uintptr_t two_mb = (uintptr_t)2 << 20;
-    const uintptr_t a = ((uintptr_t)p + two_mb - 1) & ~(two_mb - 1), b = ((uintptr_t)p + bytes) & ~(two_mb - 1);
-    if (b > a) (void)madvise((void *)a, (size_t)(b - a), MADV_HUGEPAGE);
-}
-
 int ensure_pin_ring(lda_b200_handle *h) {
     if (h->pin_slot[0]) return 0;
     for (int i = 0; i < lda_b200_handle::kStageSlots; ++i) {
@@ -1028,7 +1013,6 @@ int d2h_2d(lda_b200_handle *h, void *dst, size_t dpitch, const void *src, size_t
         return 0;
     }
     TRY(ensure_pin_ring(h));
-    advise_huge_pages(dst, (rows - 1) * dpitch + width);
     const size_t sb = lda_b200_handle::kStageSlotBytes;
     const size_t rows_per = std::max<size_t>(1, sb / width);
     if (width > sb) {  // very wide rows: let the driver stage them
@@ -1810,8 +1794,6 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
         uint64_t keep = UINT64_MAX;
         CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
         TRY(dalloc(h, &h->doc_counter, 1));
-        TRY(dalloc(h, &h->ticket, 1));
-        CU(cudaMemsetAsync(h->ticket, 0, sizeof(unsigned), h->stream));
         TRY(dalloc(h, &h->err_flag, 1));
         TRY(dalloc(h, &h->dacc, 2));
         CU(cudaMemsetAsync(h->doc_counter, 0, sizeof(int), h->stream));
@@ -1821,7 +1803,6 @@ int lda_b200_create(const lda_b200_config *cfg, int32_t device, lda_b200_handle 
             return (v == 1 || v == 2 || v == 4) ? v : dflt;
         };
         if (const char *e = getenv("LDA_B200_PAIR_MAX_DOCS")) h->pair_docs_max = atoll(e);
-        if (const char *e = getenv("LDA_B200_FUSED_NZ")) h->fused_nz = atoi(e) != 0;
         h->docs_per_warp_fit = env_gd("LDA_B200_DOCS_PER_WARP_FIT", h->docs_per_warp_fit);
         h->docs_per_warp_transform = env_gd("LDA_B200_DOCS_PER_WARP_TRANSFORM", h->docs_per_warp_transform);
         h->stage_bytes = (size_t)256 << 20;
@@ -1858,7 +1839,6 @@ void lda_b200_destroy(lda_b200_handle *h) {
     dfree(h, &h->inv_z);
     dfree(h, &h->inv_colsum);
     dfree(h, &h->doc_counter);
-    dfree(h, &h->ticket);
     dfree(h, &h->err_flag);
     dfree(h, &h->dacc);
     dfree(h, &h->rho_tab);
@@ -2274,21 +2254,12 @@ int lda_b200_fit_iterate(lda_b200_handle *h, int32_t n_iterations, lda_b200_coun
                 const int bs = blend_block(h->Kp);
                 int slot;
                 TRY(ev_begin(h, 1, &slot));
-                if (h->fused_nz) {
-                    // column sums of nPhiHat (nZHat), nZ' and invZ' in one launch: the last block to finish adds the partials
-                    TRY(ensure_partials(h, (size_t)h->sms * 2 * h->Kp));
-                    hat_colsum_nz_kernel<8><<<h->sms * 2, bs, (size_t)bs * sizeof(float4), h->stream>>>(
-                        h->nphi_hat, h->W, h->Kp, h->partials, h->ticket, h->nz, h->inv_z, h->doc_counter, h->K, Ad, Cd,
-                        cfg.eta * (double)h->W);
-                    KCHECK();
-                } else {
-                    TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
-                    hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->partials);
-                    KCHECK();
-                    nz_update_kernel<<<1, 1024, 0, h->stream>>>(h->nz, h->partials, h->sms * 4, h->inv_z, h->doc_counter, h->K, h->Kp,
-                                                               Ad, Cd, cfg.eta * (double)h->W);
-                    KCHECK();
-                }
+                TRY(ensure_partials(h, (size_t)h->sms * 4 * h->Kp));
+                hat_colsum_kernel<<<h->sms * 4, bs, (size_t)bs * sizeof(float4), h->stream>>>(h->nphi_hat, h->W, h->Kp, h->partials);
+                KCHECK();
+                nz_update_kernel<<<1, 1024, 0, h->stream>>>(h->nz, h->partials, h->sms * 4, h->inv_z, h->doc_counter, h->K, h->Kp, Ad, Cd,
+                                                           cfg.eta * (double)h->W);
+                KCHECK();
                 BlendArgs ba;
                 ba.nphi = h->nphi;
                 ba.nphi_hat = h->nphi_hat;
