@@ -1,7 +1,7 @@
 #!/bin/bash
 # third ncu pass of round 2: the paired (two tokens per butterfly) fit kernel against the unpaired one on a launch range of
-# 1,600 documents (BatchSize 100 x Processes 16, the reference's defaults on a 16-thread host), the fused column-sum + nZ
-# kernel, and the launch list of one iteration at that operating point.  Each command first runs plainly.
+# 1,600 documents (BatchSize 100 x Processes 16, the reference's defaults on a 16-thread host), and the launch list of one
+# iteration at that operating point.  Each command first runs plainly.
 set -u
 O=gpurun_out/r2c
 mkdir -p $O
@@ -12,7 +12,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k "$KERN" -c 600 --cs
 echo "launch list rc=$?"
 LDA_B200_PAIR_MAX_DOCS=0 ncu --set full --clock-control none --import-source on -k regex:scvb0_docs32 -s 30 -c 1 -o $O/prof_unpaired $P > $O/ncu_unpaired.log 2>&1
 echo "unpaired rc=$?"
-LDA_B200_PAIR_MAX_DOCS=8192 ncu --set full --clock-control none --import-source on -k regex:scvb0_docs32 -s 30 -c 1 -o $O/prof_paired $P > $O/ncu_paired.log 2>&1
+LDA_B200_PAIR_MAX_DOCS=16384 ncu --set full --clock-control none --import-source on -k regex:scvb0_docs32 -s 30 -c 1 -o $O/prof_paired $P > $O/ncu_paired.log 2>&1
 echo "paired rc=$?"
-ncu --set full --clock-control none --import-source on -k regex:hat_colsum_nz -s 30 -c 1 -o $O/prof_colsum $P > $O/ncu_colsum.log 2>&1
-echo "colsum rc=$?"
