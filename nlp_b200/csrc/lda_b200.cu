@@ -393,8 +393,11 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
     constexpr bool CAN_DET = FIT;
     const bool det = CAN_DET && a.hat_fx != nullptr;
     const int gd = det ? 1 : (FIT ? h->docs_per_warp_fit : h->docs_per_warp_transform);
-    // a launch range too small to fill the device lasts as long as its longest document: shorten the per-token chain
-    const bool pair = !det && a.pair && vecs > 16;
+    // a launch range too small to fill the device lasts as long as its longest document: shorten the per-token chain.
+    // Fit only: a fit's result depends on its schedule anyway (the order of the fp32 reductions into nPhiHat), whereas the
+    // Transform of a document must not depend on what else is in the call (test_transform_pipeline_ranges: pieces of a
+    // corpus give bitwise what the whole gives), so Transform keeps one arithmetic order whatever the launch size.
+    const bool pair = FIT && !det && a.pair && vecs > 16;
     if (!pair && gd > 1 && vecs > 16 && vecs <= 64) {
         const bool full = vecs == 32 || vecs == 64;
         const bool wide_k = vecs > 32;  // 128 < K <= 256
@@ -419,7 +422,9 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
 #define LDA_WIDE(NV, FULLK)                                                        \
     do {                                                                           \
         if (det) return wide(scvb0_docs32_kernel<NV, FULLK, FIT, CAN_DET>, NV);    \
-        if (pair) return wide(scvb0_docs32_kernel<NV, FULLK, FIT, false, true>, NV); \
+        if constexpr (FIT) {                                                       \
+            if (pair) return wide(scvb0_docs32_kernel<NV, FULLK, true, false, true>, NV); \
+        }                                                                          \
         return wide(scvb0_docs32_kernel<NV, FULLK, FIT, false>, NV);               \
     } while (0)
     if (vecs <= 4) LDA_NARROW(4);

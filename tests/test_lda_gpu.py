@@ -796,10 +796,10 @@ def test_step_issued_as_sub_range_launches(monkeypatch):
 @pytest.mark.parametrize("k,D,W,b", [(100, 300, 800, 100), (200, 120, 600, 32), (256, 300, 1000, 128), (500, 60, 500, 32),
                                      (1024, 48, 400, 16)])
 def test_throughput_kernels_on_small_corpora(k, D, W, b, monkeypatch):
-    """Launch ranges of up to LDA_B200_PAIR_MAX_DOCS documents run the two-tokens-per-butterfly kernels, larger ones the
-    throughput kernels (one token per butterfly, and for Transform at 64 < K <= 256 four documents per warp).  Whatever the
-    default threshold is, this test runs both families on the same small corpora -- fit and Transform against the oracle, and
-    the two fitted models against each other."""
+    """Fit launch ranges of up to LDA_B200_PAIR_MAX_DOCS documents run the two-tokens-per-butterfly kernels, larger ones the
+    throughput kernels (one token per butterfly).  Whatever the default threshold is, this test runs both families on the
+    same small corpora against the oracle (fit, then Transform under each fitted model), and the two fitted models against
+    each other."""
     monkeypatch.setenv("LDA_B200_PAIR_MAX_DOCS", "0")
     m = synth(D, W, 40, block=b)
     lda, o = run_pair(m, k, 4, BatchSize=b)
