@@ -397,7 +397,8 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
     // Fit only: a fit's result depends on its schedule anyway (the order of the fp32 reductions into nPhiHat), whereas the
     // Transform of a document must not depend on what else is in the call (test_transform_pipeline_ranges: pieces of a
     // corpus give bitwise what the whole gives), so Transform keeps one arithmetic order whatever the launch size.
-    const bool pair = FIT && !det && a.pair && vecs > 16;
+    // K <= 256 only: that is where it pays (measured at K = 100 and 256); at K = 1024 it made no difference
+    const bool pair = FIT && !det && a.pair && vecs > 16 && vecs <= 64;
     if (!pair && gd > 1 && vecs > 16 && vecs <= 64) {
         const bool full = vecs == 32 || vecs == 64;
         const bool wide_k = vecs > 32;  // 128 < K <= 256
@@ -423,7 +424,9 @@ int launch_docs(lda_b200_handle *h, const DocsArgs &a, const int *order, cudaStr
     do {                                                                           \
         if (det) return wide(scvb0_docs32_kernel<NV, FULLK, FIT, CAN_DET>, NV);    \
         if constexpr (FIT) {                                                       \
-            if (pair) return wide(scvb0_docs32_kernel<NV, FULLK, true, false, true>, NV); \
+            if constexpr (NV <= 2) {                                                   \
+                if (pair) return wide(scvb0_docs32_kernel<NV, FULLK, true, false, true>, NV); \
+            }                                                                          \
         }                                                                          \
         return wide(scvb0_docs32_kernel<NV, FULLK, FIT, false>, NV);               \
     } while (0)
