@@ -477,6 +477,13 @@ def ours(args):
     if rank == 0 and world == 1 and not args.skip_cpu:
         cb = cpu_run(args, D, W, K, md, 1, 0, dev)
         cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        if ref_defaults is not None:
+            # the CPU port at the reference's default BatchSize too (Processes = host cores, one minibatch each)
+            import copy
+            a100 = copy.copy(args)
+            a100.batch_size, a100.group = 100, os.cpu_count() or 1
+            cb100 = cpu_run(a100, D, W, K, md, 2, 1, dev)
+            ref_defaults["cpu_port_same_operating_point"] = {k: cb100[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {
