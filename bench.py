@@ -21,7 +21,8 @@ e2e     = the same metric through the public API call a user makes -- LatentDiri
 e2e_pageable        = the same call on pageable NumPy buffers (what a Go caller's slices are): first call on a new
                       object (cold: handle, pools, staging ring, communicator) and second call (warm).
 reference_defaults  = the fit at the reference's own defaults, BatchSize 100 (lda.go:164) and Processes = host cores
-                      (lda.go:185), and at Processes = 1.
+                      (lda.go:185), and at Processes = 1; plus the CPU port at that same operating point
+                      (cpu_port_same_operating_point, SURVEY 8d: "the CPU oracle run at the same b").
 roofline.memory_floor = the minibatch kernel's memory access mix replayed without arithmetic or dependencies
                       (lda_b200_probe_memory_mix), measured in the same process: what bounds the kernel is the L2's
                       atomic (red.add) throughput, not HBM.
